@@ -1,0 +1,190 @@
+/* nvd.h — C ABI of libnvd.so: the B200-native Monte-Carlo decode path
+ *   info bits -> convolutional encoder -> BPSK+AWGN -> neural decoder -> hard decision -> BER/FER
+ * of enessinanparildi/Neural-Network-Based-Viterbi-Decoding.
+ *
+ * The reference is pure Python and has NO FFI / plugin layer: the path sits
+ * behind module-level functions that exchange numpy arrays and whose heavy lifting is done by
+ * Python loops and a TensorFlow-1.x session.  Each entry point below names the reference
+ * function (file:line under /root/reference) whose work it replaces; the Python drop-in
+ * modules (neural-network-based-viterbi-decoding_b200/src/*.py) bind them through ctypes, and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns NVD_OK (0) or a negative nvd_status; nvd_last_error() returns a
+ *     thread-local message; no exception or abort crosses the boundary;
+ *   - plain pointers and sizes only; `*_dev` / unsuffixed buffer arguments are DEVICE pointers
+ *     (from nvd_alloc or any CUDA allocator of the same device), `*_host` are HOST pointers;
+ *   - a context owns one device, one stream, its models and scratch; calls are asynchronous on
+ *     that stream unless documented as synchronous; a context is not thread-safe, distinct
+ *     contexts are;
+ *   - there is NO CPU fallback: without a CUDA device nvd_ctx_create fails.
+ *
+ * Packed-bit wire format: frames are byte aligned; bit i (little-endian within the byte
+ * stream) of a frame is the symbol at time i.  A frame of L info bits occupies ceil(L/8)
+ * bytes, its 2L coded bits ceil(2L/8) bytes with coded[2i] = g_a(i), coded[2i+1] = g_b(i).
+ * Decoder class indices follow the reference's MSB-first labels (generate_class_bits,
+ * src/fnn_viterbi.py:283): class = bit-reverse_L(time-packed info word).
+ */
+#ifndef NVD_H_
+#define NVD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVD_VERSION 100 /* 0.1.0 */
+
+typedef struct nvd_ctx nvd_ctx;
+
+typedef enum {
+  NVD_OK = 0,
+  NVD_ERR_INVALID = -1,     /* bad argument */
+  NVD_ERR_CUDA = -2,        /* CUDA runtime / launch failure (message has the CUDA error) */
+  NVD_ERR_OOM = -3,
+  NVD_ERR_UNSUPPORTED = -4, /* shape not covered by a compiled kernel */
+  NVD_ERR_DEVICE_TIMEOUT = -5 /* a bounded on-device wait expired (kernel self-aborted) */
+} nvd_status;
+
+/* encoder selection — src/fnn_viterbi.py:122 (encode_57), :157 (encode_133171) */
+enum { NVD_CODE_57_REF = 0, NVD_CODE_133171 = 1, NVD_CODE_57_CAUSAL = 2 };
+/* channel output storage — float32 rows (src/fnn_viterbi.py:373,384), bf16 for the tensor-core
+ * path, or the int32 truncation of src/fnn_viterbi_bitwise.py:309-317 / src/rnn_viterbi.py:201-208 */
+enum { NVD_F32 = 0, NVD_BF16 = 1, NVD_I32_TRUNC = 2 };
+/* activations — tanh src/fnn_viterbi.py:496-508, relu src/fnn_viterbi_bitwise.py:388,397 */
+enum { NVD_ACT_IDENTITY = 0, NVD_ACT_TANH = 1, NVD_ACT_RELU = 2 };
+/* arithmetic of the decoder forward */
+enum { NVD_PREC_FP32 = 0, NVD_PREC_BF16_TC = 1 };
+/* Monte-Carlo pipeline organisation */
+enum { NVD_MC_STAGED = 0, NVD_MC_FUSED = 1 };
+/* nvd_count_errors flags */
+enum { NVD_COUNT_PRED_IS_MSB_CLASS = 1 };
+
+/* ---- library / context ------------------------------------------------------------------ */
+int nvd_version(void);
+const char* nvd_last_error(void);
+int nvd_device_count(int* count);
+/* replaces the implicit `tf.Session()` device/state (src/fnn_viterbi.py:570) */
+int nvd_ctx_create(int device, uint64_t seed, nvd_ctx** out);
+int nvd_ctx_destroy(nvd_ctx* ctx);
+int nvd_set_seed(nvd_ctx* ctx, uint64_t seed);
+int nvd_sync(nvd_ctx* ctx);                         /* synchronous; reports device-side aborts */
+int nvd_device_info(nvd_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- memory and timing (the caller owns what it allocates) ------------------------------- */
+int nvd_alloc(nvd_ctx* ctx, size_t bytes, void** dptr);
+int nvd_free(nvd_ctx* ctx, void* dptr);
+int nvd_host_alloc(nvd_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int nvd_host_free(nvd_ctx* ctx, void* hptr);
+int nvd_memcpy_h2d(nvd_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int nvd_memcpy_d2h(nvd_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int nvd_memset(nvd_ctx* ctx, void* dst_dev, int byte, size_t bytes);
+int nvd_event_create(nvd_ctx* ctx, void** event);
+int nvd_event_record(nvd_ctx* ctx, void* event);    /* on the context's stream */
+int nvd_event_elapsed_ms(nvd_ctx* ctx, void* start, void* stop, float* ms); /* synchronises on stop */
+int nvd_event_destroy(nvd_ctx* ctx, void* event);
+
+/* ---- K0 source: class-balanced / random info words ---------------------------------------
+ * replaces generate_class_bits rows repeated per class (src/fnn_viterbi.py:380-388) for L <= 16
+ * (frame f carries class f mod 2^L) and np.random.randint (src/fnn_viterbi_bitwise.py:239-250)
+ * for L > 16 (Philox stream 2).  info_packed: [B, ceil(L/8)] bytes. */
+int nvd_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed);
+
+/* ---- K1 encoder: replaces encode_57 / encode_133171 (src/fnn_viterbi.py:122-217) and, with the
+ * 6 state bits prepended by the host, encode_133171_with_state (src/fnn_viterbi_bitwise.py:141-215).
+ * info_packed [B, ceil(L/8)] -> coded_packed [B, ceil(2L/8)].  Zero state, unterminated. */
+int nvd_encode(nvd_ctx* ctx, int code, const uint8_t* info_packed, int L, int64_t B,
+               uint8_t* coded_packed);
+
+/* ---- K2 channel: replaces modulate_awgn (src/fnn_viterbi.py:224-253) + the per-frame Python
+ * loops that call it (:380-388).  y[b, j] = (2c-1) + sigma * N(0,1), noise = Philox4x32-10 keyed
+ * by (seed; frame0+b, j/4, snr_idx).  y is [B, n] dense in out_dtype (NVD_F32/BF16/I32_TRUNC). */
+int nvd_channel(nvd_ctx* ctx, const uint8_t* coded_packed, int n, int64_t B, float sigma,
+                int snr_idx, uint64_t frame0, int out_dtype, void* y);
+
+/* ---- K3 feed-forward decoder: replaces initialize_weights + multilayer_perceptron + tf.argmax
+ * (src/fnn_viterbi.py:413-510,606-610; src/fnn_viterbi_bitwise.py:326-399,504;
+ *  src/fnn_viterbi_seq_predict.py:343-414).  W[l] is [dims[l], dims[l+1]] row-major (x@W+b),
+ * host pointers; returns a model handle. */
+int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts,
+                 const float* const* W_host, const float* const* b_host, int* model);
+int nvd_mlp_free(nvd_ctx* ctx, int model);
+/* y: [B, dims[0]] in y_dtype.  soft_out: [B, dims[n]] fp32 or NULL.  hard_out: argmax class
+ * (first index on ties) as hard_bytes-wide (1, 2 or 4) little-endian integers, or NULL.
+ * NVD_PREC_BF16_TC needs a tcgen05-covered shape (see nvd_mlp_tc_supported). */
+int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t B, int precision,
+                    float* soft_out, void* hard_out, int hard_bytes);
+int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported);
+/* host-buffer convenience (synchronous): the `predictions_tensor.eval(feed_dict={x: test_set})`
+ * call of src/fnn_viterbi.py:610 — chunked H2D, forward, D2H.  y_host fp32 [B, dims[0]]. */
+int nvd_mlp_decode_host(nvd_ctx* ctx, int model, const float* y_host, int64_t B, int precision,
+                        float* soft_host, int32_t* hard_host);
+
+/* ---- K4 recurrent decoder: replaces build_seq2seq_model's forward (src/rnn_viterbi.py:278-305).
+ * LSTMCell semantics: gates i,j,f,o, forget_bias 1; kernels [1+H, 4H]; linear [H]->1. */
+int nvd_lstm_load(nvd_ctx* ctx, int H, const float* enc_W, const float* enc_b, const float* dec_W,
+                  const float* dec_b, const float* lin_w, const float* lin_b, int* model);
+int nvd_lstm_free(nvd_ctx* ctx, int model);
+/* y [B, T_enc] in y_dtype; dec_in [B, T_dec] fp32 (teacher forcing, src/rnn_viterbi.py:362-371)
+ * or NULL = autoregressive (previous hard decision fed back, first input EOS=1).
+ * logits_out [B, T_dec] fp32 or NULL; hard_packed [B, ceil(T_dec/8)] (bit t = logit_t > 0) or NULL.
+ * fast_math != 0 uses MUFU tanh/sigmoid approximations. */
+int nvd_lstm_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, const float* dec_in,
+                     int T_enc, int T_dec, int64_t B, int fast_math, float* logits_out,
+                     uint8_t* hard_packed);
+
+/* ---- K5 reduction: replaces calculate_error (src/fnn_viterbi.py:619-674) and calculate_ber /
+ * calculate_hamming_distance_decimal (src/fnn_viterbi_mixed_snr.py:303-328,634-655).
+ * pred, label: [B, stride_bytes] little-endian packed frames, L valid bits each.
+ * counters_dev: uint64[4] = {bit_errors, frame_errors, frames, bits}, ACCUMULATED into.
+ * flag NVD_COUNT_PRED_IS_MSB_CLASS: pred holds MSB-first class indices (stride <= 4), label
+ * time-packed info words. */
+int nvd_count_errors(nvd_ctx* ctx, const void* pred, const void* label, int stride_bytes, int L,
+                     int64_t B, int flags, uint64_t* counters_dev);
+
+/* ---- whole Monte-Carlo step ---------------------------------------------------------------
+ * replaces the test half of train_test_dataset + the test-set forward + calculate_error
+ * (src/fnn_viterbi.py:380-388,606-610,619-674) / get_dataset + create_model_graph eval branch
+ * (src/fnn_viterbi_mixed_snr.py:452-460,806-845).  Frames [frame0, frame0+frames) at each of the
+ * n_snr points; results are independent of how a frame range is split across calls or GPUs. */
+typedef struct {
+  int32_t struct_bytes;   /* = sizeof(nvd_mc_config) */
+  int32_t model;          /* MLP handle */
+  int32_t code;           /* NVD_CODE_* */
+  int32_t L;              /* info bits per frame (<= 16 for class decoders) */
+  int32_t precision;      /* NVD_PREC_* */
+  int32_t mode;           /* NVD_MC_STAGED | NVD_MC_FUSED (fused needs BF16_TC + covered shape) */
+  int32_t y_dtype;        /* staged: storage of the channel output (NVD_F32 / NVD_BF16) */
+  int32_t reserved;
+  uint64_t frame0;
+  uint64_t frames;
+} nvd_mc_config;
+/* asynchronous; counters_dev: uint64 [n_snr][4], accumulated into. snr_idx[i] keys the noise. */
+int nvd_mc_run(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host,
+               const int32_t* snr_idx_host, int n_snr, uint64_t* counters_dev);
+/* synchronous host-buffer form (the end-to-end call): info words come from the host, hard
+ * decisions and counters go back.  info_host [B, ceil(L/8)], pred_host [B] uint8 class indices
+ * (may be NULL), counters_host uint64[4] (overwritten). */
+int nvd_mc_run_host(nvd_ctx* ctx, const nvd_mc_config* cfg, float snr_db, int snr_idx,
+                    const uint8_t* info_host, uint8_t* pred_host, uint64_t* counters_host);
+/* per-stage device milliseconds of the most recent staged nvd_mc_run chunk sequence:
+ * ms[5] = {source, encode, channel, decode, count} (sums over chunks), synchronises. */
+int nvd_mc_stage_ms(nvd_ctx* ctx, float* ms5);
+/* per-stage timing makes staged nvd_mc_run synchronise after every chunk; off by default. */
+int nvd_mc_set_stage_timing(nvd_ctx* ctx, int enabled);
+
+/* ---- diagnostics ---------------------------------------------------------------------------
+ * One tcgen05.mma (M=128, K=16, bf16 x bf16 -> fp32) on caller-supplied raw shared-memory images
+ * and descriptor strides; used by tests/test_gpu_umma_probe.py to pin the UMMA shared-memory
+ * layout the tensor-core kernel relies on.  a_image_host: 4096 B, b_image_host: N*32 B,
+ * d_host: [128, N] fp32. */
+int nvd_debug_umma_probe(nvd_ctx* ctx, int N, int a_lbo_bytes, int a_sbo_bytes, int b_lbo_bytes,
+                         int b_sbo_bytes, const void* a_image_host, const void* b_image_host,
+                         float* d_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVD_H_ */

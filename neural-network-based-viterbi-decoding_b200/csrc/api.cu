@@ -1,0 +1,587 @@
+// api.cu — the C ABI of libnvd.so (include/nvd.h): context, memory, model registry and the
+// Monte-Carlo step orchestration (staged: K0 -> K1 -> K2 -> K3 -> K5 through HBM; fused: one
+// persistent tcgen05 kernel, see k_mlp_tc.cu).  Everything here is host code; there is no CPU
+// compute path — without a CUDA device nvd_ctx_create fails.
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+
+namespace nvd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_scratch(nvd_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return NVD_OK;
+  if (ctx->scratch) {
+    NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+    NVD_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  NVD_CUDA(cudaMalloc(&ctx->scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return NVD_OK;
+}
+
+static int check_abort(nvd_ctx* ctx) {
+  if (ctx->abort_flag_host && *ctx->abort_flag_host) {
+    const int code = *ctx->abort_flag_host;
+    *ctx->abort_flag_host = 0;
+    cudaMemsetAsync(ctx->abort_flag, 0, sizeof(int), ctx->stream);
+    set_error("device-side bounded wait expired (code %d): tcgen05 pipeline aborted itself", code);
+    return NVD_ERR_DEVICE_TIMEOUT;
+  }
+  return NVD_OK;
+}
+
+static float sigma_of_db(float snr_db) {
+  // sigma = sqrt(1 / (2 * 10^(dB/10)))   /root/reference/src/fnn_viterbi.py:89-92
+  return static_cast<float>(std::sqrt(0.5 / std::pow(10.0, static_cast<double>(snr_db) / 10.0)));
+}
+
+}  // namespace nvd
+
+using namespace nvd;
+
+#define CTX_GUARD(ctx)                                        \
+  NVD_REQUIRE((ctx) != nullptr, "null context");              \
+  NVD_CUDA(cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+int nvd_version(void) { return NVD_VERSION; }
+const char* nvd_last_error(void) { return g_err; }
+
+int nvd_device_count(int* count) {
+  NVD_REQUIRE(count != nullptr, "null count");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return NVD_ERR_CUDA;
+  }
+  *count = n;
+  return NVD_OK;
+}
+
+int nvd_ctx_create(int device, uint64_t seed, nvd_ctx** out) {
+  NVD_REQUIRE(out != nullptr, "null out");
+  *out = nullptr;
+  int n = 0;
+  NVD_CUDA(cudaGetDeviceCount(&n));
+  NVD_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d); libnvd has no CPU fallback", device, n);
+  NVD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NVD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libnvd is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return NVD_ERR_UNSUPPORTED;
+  }
+  nvd_ctx* ctx = new (std::nothrow) nvd_ctx();
+  if (!ctx) { set_error("out of host memory"); return NVD_ERR_OOM; }
+  ctx->device = device;
+  ctx->seed = seed;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->abort_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->abort_flag, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->abort_flag_host, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->counters_scratch, 4 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->counters_pinned, 4 * sizeof(uint64_t));
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->stage_ev[i]);
+  if (e != cudaSuccess) {
+    set_error("context creation failed: %s", cudaGetErrorString(e));
+    nvd_ctx_destroy(ctx);
+    return NVD_ERR_CUDA;
+  }
+  *ctx->abort_flag_host = 0;
+  *out = ctx;
+  return NVD_OK;
+}
+
+int nvd_ctx_destroy(nvd_ctx* ctx) {
+  if (!ctx) return NVD_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& m : ctx->mlps) {
+    for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m.W[l]); cudaFree(m.b[l]); }
+    cudaFree(m.tc_image);
+    cudaFree(m.tc_bias_out);
+  }
+  for (auto& m : ctx->lstms) cudaFree(m.blob);
+  cudaFree(ctx->scratch);
+  cudaFree(ctx->mc_buf);
+  cudaFree(ctx->abort_flag);
+  cudaFree(ctx->counters_scratch);
+  if (ctx->abort_flag_host) cudaFreeHost(ctx->abort_flag_host);
+  if (ctx->counters_pinned) cudaFreeHost(ctx->counters_pinned);
+  if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+  for (int i = 0; i < 6; ++i)
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NVD_OK;
+}
+
+int nvd_set_seed(nvd_ctx* ctx, uint64_t seed) {
+  NVD_REQUIRE(ctx != nullptr, "null context");
+  ctx->seed = seed;
+  return NVD_OK;
+}
+
+int nvd_sync(nvd_ctx* ctx) {
+  CTX_GUARD(ctx);
+  NVD_CUDA(cudaMemcpyAsync(ctx->abort_flag_host, ctx->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return check_abort(ctx);
+}
+
+int nvd_device_info(nvd_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  NVD_REQUIRE(ctx != nullptr, "null context");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return NVD_OK;
+}
+
+// ---- memory / timing -------------------------------------------------------------------------
+int nvd_alloc(nvd_ctx* ctx, size_t bytes, void** dptr) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(dptr != nullptr, "null dptr");
+  *dptr = nullptr;
+  if (bytes == 0) return NVD_OK;
+  NVD_CUDA(cudaMalloc(dptr, bytes));
+  return NVD_OK;
+}
+int nvd_free(nvd_ctx* ctx, void* dptr) {
+  CTX_GUARD(ctx);
+  if (dptr) {
+    NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+    NVD_CUDA(cudaFree(dptr));
+  }
+  return NVD_OK;
+}
+int nvd_host_alloc(nvd_ctx* ctx, size_t bytes, void** hptr) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(hptr != nullptr, "null hptr");
+  *hptr = nullptr;
+  if (bytes == 0) return NVD_OK;
+  NVD_CUDA(cudaMallocHost(hptr, bytes));
+  return NVD_OK;
+}
+int nvd_host_free(nvd_ctx* ctx, void* hptr) {
+  CTX_GUARD(ctx);
+  if (hptr) NVD_CUDA(cudaFreeHost(hptr));
+  return NVD_OK;
+}
+int nvd_memcpy_h2d(nvd_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_GUARD(ctx);
+  if (bytes) NVD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NVD_OK;
+}
+int nvd_memcpy_d2h(nvd_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_GUARD(ctx);
+  if (bytes) NVD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return NVD_OK;
+}
+int nvd_memset(nvd_ctx* ctx, void* dst, int byte, size_t bytes) {
+  CTX_GUARD(ctx);
+  if (bytes) NVD_CUDA(cudaMemsetAsync(dst, byte, bytes, ctx->stream));
+  return NVD_OK;
+}
+int nvd_event_create(nvd_ctx* ctx, void** event) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(event != nullptr, "null event");
+  cudaEvent_t ev;
+  NVD_CUDA(cudaEventCreate(&ev));
+  *event = ev;
+  return NVD_OK;
+}
+int nvd_event_record(nvd_ctx* ctx, void* event) {
+  CTX_GUARD(ctx);
+  NVD_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), ctx->stream));
+  return NVD_OK;
+}
+int nvd_event_elapsed_ms(nvd_ctx* ctx, void* start, void* stop, float* ms) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(ms != nullptr, "null ms");
+  NVD_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+  NVD_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  return NVD_OK;
+}
+int nvd_event_destroy(nvd_ctx* ctx, void* event) {
+  CTX_GUARD(ctx);
+  if (event) NVD_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return NVD_OK;
+}
+
+// ---- K0 / K1 / K2 / K5 ------------------------------------------------------------------------
+int nvd_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(L >= 1 && L <= (1 << 24), "L=%d out of range", L);
+  NVD_REQUIRE(B >= 0 && (B == 0 || info_packed), "bad B / null buffer");
+  return launch_source(ctx, L, frame0, B, info_packed);
+}
+
+int nvd_encode(nvd_ctx* ctx, int code, const uint8_t* info_packed, int L, int64_t B, uint8_t* coded_packed) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(code == NVD_CODE_57_REF || code == NVD_CODE_133171 || code == NVD_CODE_57_CAUSAL, "unknown code %d", code);
+  NVD_REQUIRE(L >= 1, "L=%d out of range", L);
+  NVD_REQUIRE(B >= 0 && (B == 0 || (info_packed && coded_packed)), "bad B / null buffer");
+  return launch_encode(ctx, code, info_packed, L, B, coded_packed);
+}
+
+int nvd_channel(nvd_ctx* ctx, const uint8_t* coded_packed, int n, int64_t B, float sigma, int snr_idx,
+                uint64_t frame0, int out_dtype, void* y) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(n >= 1, "n=%d out of range", n);
+  NVD_REQUIRE(snr_idx >= 0 && snr_idx < (1 << 24), "snr_idx=%d out of range", snr_idx);
+  NVD_REQUIRE(B >= 0 && (B == 0 || (coded_packed && y)), "bad B / null buffer");
+  NVD_REQUIRE(sigma >= 0.0f && std::isfinite(sigma), "sigma must be finite and >= 0");
+  return launch_channel(ctx, coded_packed, n, B, sigma, snr_idx, frame0, out_dtype, y);
+}
+
+int nvd_count_errors(nvd_ctx* ctx, const void* pred, const void* label, int stride_bytes, int L, int64_t B,
+                     int flags, uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(stride_bytes >= 1 && L >= 1 && L <= 8 * stride_bytes, "L=%d does not fit stride %d", L, stride_bytes);
+  NVD_REQUIRE(!(flags & NVD_COUNT_PRED_IS_MSB_CLASS) || stride_bytes <= 4, "MSB class flag needs stride <= 4");
+  NVD_REQUIRE(B >= 0 && counters_dev && (B == 0 || (pred && label)), "bad B / null buffer");
+  return launch_count(ctx, pred, label, stride_bytes, L, B, flags, counters_dev);
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------
+int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts, const float* const* W_host,
+                 const float* const* b_host, int* model) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(model != nullptr && dims && acts && W_host && b_host, "null argument");
+  NVD_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, "n_layers=%d out of range (1..%d)", n_layers, kMaxLayers);
+  for (int l = 0; l <= n_layers; ++l) NVD_REQUIRE(dims[l] >= 1 && dims[l] <= 65536, "dims[%d]=%d out of range", l, dims[l]);
+  for (int l = 0; l < n_layers; ++l)
+    NVD_REQUIRE(acts[l] >= NVD_ACT_IDENTITY && acts[l] <= NVD_ACT_RELU && W_host[l] && b_host[l], "bad layer %d", l);
+  MlpModel m;
+  m.live = true;
+  m.n_layers = n_layers;
+  for (int l = 0; l <= n_layers; ++l) m.dims[l] = dims[l];
+  for (int l = 0; l < n_layers; ++l) {
+    m.acts[l] = acts[l];
+    const size_t wb = static_cast<size_t>(dims[l]) * dims[l + 1] * sizeof(float);
+    NVD_CUDA(cudaMalloc(&m.W[l], wb));
+    NVD_CUDA(cudaMalloc(&m.b[l], dims[l + 1] * sizeof(float)));
+    NVD_CUDA(cudaMemcpy(m.W[l], W_host[l], wb, cudaMemcpyHostToDevice));
+    NVD_CUDA(cudaMemcpy(m.b[l], b_host[l], dims[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (tc_shape_supported(m)) NVD_TRY(tc_build_image(ctx, m, W_host, b_host));
+  ctx->mlps.push_back(m);
+  *model = static_cast<int>(ctx->mlps.size()) - 1;
+  return NVD_OK;
+}
+
+static int get_mlp(nvd_ctx* ctx, int model, MlpModel** out) {
+  NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->mlps.size()) && ctx->mlps[model].live, "bad MLP handle %d", model);
+  *out = &ctx->mlps[model];
+  return NVD_OK;
+}
+
+int nvd_mlp_free(nvd_ctx* ctx, int model) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->W[l]); cudaFree(m->b[l]); m->W[l] = m->b[l] = nullptr; }
+  cudaFree(m->tc_image); m->tc_image = nullptr;
+  cudaFree(m->tc_bias_out); m->tc_bias_out = nullptr;
+  m->live = false;
+  return NVD_OK;
+}
+
+int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported) {
+  NVD_REQUIRE(ctx && supported, "null argument");
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  *supported = m->tc_image ? 1 : 0;
+  return NVD_OK;
+}
+
+int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t B, int precision,
+                    float* soft_out, void* hard_out, int hard_bytes) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  NVD_REQUIRE(B >= 0 && (B == 0 || y), "bad B / null input");
+  NVD_REQUIRE(y_dtype == NVD_F32 || y_dtype == NVD_BF16 || y_dtype == NVD_I32_TRUNC, "unknown y_dtype %d", y_dtype);
+  NVD_REQUIRE(!hard_out || hard_bytes == 1 || hard_bytes == 2 || hard_bytes == 4, "hard_bytes must be 1, 2 or 4");
+  NVD_REQUIRE(!hard_out || hard_bytes == 4 || m->dims[m->n_layers] <= (1 << (8 * hard_bytes)), "class index does not fit hard_bytes");
+  if (precision == NVD_PREC_FP32) return launch_mlp_fp32(ctx, *m, y, y_dtype, B, soft_out, hard_out, hard_bytes);
+  if (precision == NVD_PREC_BF16_TC) {
+    if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
+    NVD_REQUIRE(y_dtype == NVD_BF16, "BF16_TC path takes bf16 inputs (TMA-staged activations)");
+    return launch_mlp_tc_staged(ctx, *m, static_cast<const __nv_bfloat16*>(y), B, soft_out, hard_out, hard_bytes);
+  }
+  set_error("unknown precision %d", precision);
+  return NVD_ERR_INVALID;
+}
+
+// fp32 -> bf16 on device for the host-buffer tensor-core path
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+int nvd_mlp_decode_host(nvd_ctx* ctx, int model, const float* y_host, int64_t B, int precision, float* soft_host,
+                        int32_t* hard_host) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  NVD_REQUIRE(B >= 0 && (B == 0 || y_host), "bad B / null input");
+  if (B == 0) return NVD_OK;
+  const int n_in = m->dims[0], n_out = m->dims[m->n_layers];
+  const int64_t chunk = std::min<int64_t>(B, 1 << 20);
+  const size_t in_b = static_cast<size_t>(chunk) * n_in * 4, in16_b = static_cast<size_t>(chunk) * n_in * 2;
+  const size_t soft_b = soft_host ? static_cast<size_t>(chunk) * n_out * 4 : 0;
+  const size_t hard_b = static_cast<size_t>(chunk) * 4;
+  const size_t need = in_b + in16_b + soft_b + hard_b + 1024;
+  if (need > ctx->mc_buf_bytes) {
+    NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->mc_buf);
+    ctx->mc_buf = nullptr; ctx->mc_buf_bytes = 0;
+    NVD_CUDA(cudaMalloc(&ctx->mc_buf, need));
+    ctx->mc_buf_bytes = need;
+  }
+  char* base = static_cast<char*>(ctx->mc_buf);
+  float* d_in = reinterpret_cast<float*>(base);
+  __nv_bfloat16* d_in16 = reinterpret_cast<__nv_bfloat16*>(base + in_b);
+  float* d_soft = soft_host ? reinterpret_cast<float*>(base + in_b + ((in16_b + 255) & ~size_t(255))) : nullptr;
+  int32_t* d_hard = reinterpret_cast<int32_t*>(base + in_b + ((in16_b + 255) & ~size_t(255)) + ((soft_b + 255) & ~size_t(255)));
+  for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+    const int64_t rows = std::min<int64_t>(chunk, B - r0);
+    NVD_CUDA(cudaMemcpyAsync(d_in, y_host + r0 * n_in, static_cast<size_t>(rows) * n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (precision == NVD_PREC_BF16_TC) {
+      if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
+      const int64_t n = rows * n_in;
+      f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_in16, n);
+      NVD_CHECK_LAUNCH();
+      NVD_TRY(launch_mlp_tc_staged(ctx, *m, d_in16, rows, d_soft, hard_host ? d_hard : nullptr, 4));
+    } else {
+      NVD_TRY(launch_mlp_fp32(ctx, *m, d_in, NVD_F32, rows, d_soft, hard_host ? d_hard : nullptr, 4));
+    }
+    if (soft_host) NVD_CUDA(cudaMemcpyAsync(soft_host + r0 * n_out, d_soft, static_cast<size_t>(rows) * n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hard_host) NVD_CUDA(cudaMemcpyAsync(hard_host + r0, d_hard, static_cast<size_t>(rows) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NVD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_* are reused by the next chunk
+  }
+  return nvd_sync(ctx);
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------
+static void pack_cell(int H, const float* W, const float* b, float* dst) {
+  // dst: Wp[(1+H)][H] float4 (i,j,f,o) then b4[H] float4, forget bias folded (LSTMCell forget_bias=1.0)
+  for (int k = 0; k < 1 + H; ++k)
+    for (int u = 0; u < H; ++u)
+      for (int g = 0; g < 4; ++g) dst[((k * H) + u) * 4 + g] = W[k * 4 * H + g * H + u];
+  float* b4 = dst + (1 + H) * H * 4;
+  for (int u = 0; u < H; ++u)
+    for (int g = 0; g < 4; ++g) b4[u * 4 + g] = b[g * H + u] + (g == 2 ? 1.0f : 0.0f);
+}
+
+int nvd_lstm_load(nvd_ctx* ctx, int H, const float* enc_W, const float* enc_b, const float* dec_W, const float* dec_b,
+                  const float* lin_w, const float* lin_b, int* model) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(model && enc_W && enc_b && dec_W && dec_b && lin_w && lin_b, "null argument");
+  NVD_REQUIRE(H == 16 || H == 20 || H == 32, "hidden size %d has no compiled kernel (16, 20, 32)", H);
+  const size_t cell = static_cast<size_t>((1 + H) * H + H) * 4;
+  std::vector<float> blob(2 * cell + H + 1);
+  pack_cell(H, enc_W, enc_b, blob.data());
+  pack_cell(H, dec_W, dec_b, blob.data() + cell);
+  for (int u = 0; u < H; ++u) blob[2 * cell + u] = lin_w[u];
+  blob[2 * cell + H] = lin_b[0];
+  LstmModel m;
+  m.live = true;
+  m.H = H;
+  m.blob_floats = blob.size();
+  NVD_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
+  NVD_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->lstms.push_back(m);
+  *model = static_cast<int>(ctx->lstms.size()) - 1;
+  return NVD_OK;
+}
+
+int nvd_lstm_free(nvd_ctx* ctx, int model) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[model].live, "bad LSTM handle %d", model);
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->lstms[model].blob);
+  ctx->lstms[model].blob = nullptr;
+  ctx->lstms[model].live = false;
+  return NVD_OK;
+}
+
+int nvd_lstm_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, const float* dec_in, int T_enc, int T_dec,
+                     int64_t B, int fast_math, float* logits_out, uint8_t* hard_packed) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[model].live, "bad LSTM handle %d", model);
+  NVD_REQUIRE(T_enc >= 1 && T_dec >= 1 && B >= 0 && (B == 0 || y), "bad shape / null input");
+  return launch_lstm(ctx, ctx->lstms[model], y, y_dtype, dec_in, T_enc, T_dec, B, fast_math, logits_out, hard_packed);
+}
+
+// ---- Monte-Carlo step ---------------------------------------------------------------------------
+static int validate_mc(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel** m) {
+  NVD_REQUIRE(cfg && cfg->struct_bytes == static_cast<int32_t>(sizeof(nvd_mc_config)), "bad nvd_mc_config (struct_bytes)");
+  NVD_TRY(get_mlp(ctx, cfg->model, m));
+  NVD_REQUIRE(cfg->L >= 1 && cfg->L <= 8, "Monte-Carlo class decoders support L <= 8 (got %d)", cfg->L);
+  NVD_REQUIRE((*m)->dims[0] == 2 * cfg->L, "model input width %d != 2L = %d", (*m)->dims[0], 2 * cfg->L);
+  NVD_REQUIRE((*m)->dims[(*m)->n_layers] == (1 << cfg->L), "model output width %d != 2^L", (*m)->dims[(*m)->n_layers]);
+  NVD_REQUIRE(cfg->code == NVD_CODE_57_REF || cfg->code == NVD_CODE_133171 || cfg->code == NVD_CODE_57_CAUSAL, "unknown code %d", cfg->code);
+  NVD_REQUIRE(cfg->mode == NVD_MC_STAGED || cfg->mode == NVD_MC_FUSED, "unknown mode %d", cfg->mode);
+  if (cfg->mode == NVD_MC_FUSED || cfg->precision == NVD_PREC_BF16_TC) {
+    if (!(*m)->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", cfg->model); return NVD_ERR_UNSUPPORTED; }
+  }
+  if (cfg->mode == NVD_MC_FUSED) NVD_REQUIRE(cfg->precision == NVD_PREC_BF16_TC, "fused mode runs on the BF16 tensor-core path");
+  if (cfg->mode == NVD_MC_STAGED && cfg->precision == NVD_PREC_BF16_TC)
+    NVD_REQUIRE(cfg->y_dtype == NVD_BF16, "staged BF16_TC needs y_dtype = NVD_BF16");
+  NVD_REQUIRE(cfg->y_dtype == NVD_F32 || cfg->y_dtype == NVD_BF16, "y_dtype must be NVD_F32 or NVD_BF16");
+  return NVD_OK;
+}
+
+static int ensure_mc_buf(nvd_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->mc_buf_bytes) return NVD_OK;
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->mc_buf);
+  ctx->mc_buf = nullptr;
+  ctx->mc_buf_bytes = 0;
+  NVD_CUDA(cudaMalloc(&ctx->mc_buf, bytes));
+  ctx->mc_buf_bytes = bytes;
+  return NVD_OK;
+}
+
+struct McBuffers {
+  uint8_t* info; uint8_t* coded; void* y; uint8_t* pred; int64_t chunk;
+};
+
+static int carve_mc(nvd_ctx* ctx, int L, int y_dtype, int64_t frames, McBuffers* b) {
+  const int64_t chunk = std::min<int64_t>(frames, int64_t(1) << 24);
+  const size_t S_in = (L + 7) / 8, S_out = (2 * L + 7) / 8, ys = (y_dtype == NVD_BF16 ? 2 : 4) * 2 * L;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_info = 0, o_coded = o_info + al(chunk * S_in), o_y = o_coded + al(chunk * S_out);
+  const size_t o_pred = o_y + al(chunk * ys), total = o_pred + al(chunk);
+  NVD_TRY(ensure_mc_buf(ctx, total));
+  char* base = static_cast<char*>(ctx->mc_buf);
+  b->info = reinterpret_cast<uint8_t*>(base + o_info);
+  b->coded = reinterpret_cast<uint8_t*>(base + o_coded);
+  b->y = base + o_y;
+  b->pred = reinterpret_cast<uint8_t*>(base + o_pred);
+  b->chunk = chunk;
+  return NVD_OK;
+}
+
+// one chunk of the staged pipeline; info already in b.info when have_info
+static int staged_chunk(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m, const McBuffers& b, float sigma, int snr_idx,
+                        uint64_t frame0, int64_t n, bool have_info, uint64_t* counters, bool timing) {
+  const int L = cfg->L;
+  cudaEvent_t* ev = ctx->stage_ev;
+  if (timing) cudaEventRecord(ev[0], ctx->stream);
+  if (!have_info) NVD_TRY(launch_source(ctx, L, frame0, n, b.info));
+  if (timing) cudaEventRecord(ev[1], ctx->stream);
+  NVD_TRY(launch_encode(ctx, cfg->code, b.info, L, n, b.coded));
+  if (timing) cudaEventRecord(ev[2], ctx->stream);
+  NVD_TRY(launch_channel(ctx, b.coded, 2 * L, n, sigma, snr_idx, frame0, cfg->y_dtype, b.y));
+  if (timing) cudaEventRecord(ev[3], ctx->stream);
+  if (cfg->precision == NVD_PREC_BF16_TC)
+    NVD_TRY(launch_mlp_tc_staged(ctx, *m, static_cast<const __nv_bfloat16*>(b.y), n, nullptr, b.pred, 1));
+  else
+    NVD_TRY(launch_mlp_fp32(ctx, *m, b.y, cfg->y_dtype, n, nullptr, b.pred, 1));
+  if (timing) cudaEventRecord(ev[4], ctx->stream);
+  NVD_TRY(launch_count(ctx, b.pred, b.info, 1, L, n, NVD_COUNT_PRED_IS_MSB_CLASS, counters));
+  if (timing) {
+    cudaEventRecord(ev[5], ctx->stream);
+    NVD_CUDA(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      ctx->stage_ms[i] += ms;
+    }
+  }
+  return NVD_OK;
+}
+
+int nvd_mc_run(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host, int n_snr,
+               uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(validate_mc(ctx, cfg, &m));
+  NVD_REQUIRE(snr_db_host && counters_dev && n_snr >= 1, "null argument / n_snr < 1");
+  if (cfg->frames == 0) return NVD_OK;
+  if (cfg->mode == NVD_MC_FUSED) {
+    for (int i = 0; i < n_snr; ++i) {
+      const int idx = snr_idx_host ? snr_idx_host[i] : i;
+      NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db_host[i]), idx, cfg->frame0, cfg->frames,
+                                  counters_dev + 4 * i));
+    }
+    return NVD_OK;
+  }
+  McBuffers b;
+  NVD_TRY(carve_mc(ctx, cfg->L, cfg->y_dtype, static_cast<int64_t>(cfg->frames), &b));
+  for (int i = 0; i < 5; ++i) ctx->stage_ms[i] = 0;
+  for (int i = 0; i < n_snr; ++i) {
+    const int idx = snr_idx_host ? snr_idx_host[i] : i;
+    const float sigma = sigma_of_db(snr_db_host[i]);
+    for (uint64_t done = 0; done < cfg->frames; done += b.chunk) {
+      const int64_t n = static_cast<int64_t>(std::min<uint64_t>(b.chunk, cfg->frames - done));
+      NVD_TRY(staged_chunk(ctx, cfg, m, b, sigma, idx, cfg->frame0 + done, n, false, counters_dev + 4 * i, ctx->stage_timing));
+    }
+  }
+  return NVD_OK;
+}
+
+int nvd_mc_set_stage_timing(nvd_ctx* ctx, int enabled) {
+  NVD_REQUIRE(ctx != nullptr, "null context");
+  ctx->stage_timing = enabled != 0;
+  return NVD_OK;
+}
+
+int nvd_mc_stage_ms(nvd_ctx* ctx, float* ms5) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(ms5 != nullptr, "null ms5");
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 5; ++i) ms5[i] = ctx->stage_ms[i];
+  return NVD_OK;
+}
+
+int nvd_mc_run_host(nvd_ctx* ctx, const nvd_mc_config* cfg, float snr_db, int snr_idx, const uint8_t* info_host,
+                    uint8_t* pred_host, uint64_t* counters_host) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(validate_mc(ctx, cfg, &m));
+  NVD_REQUIRE(info_host && counters_host, "null argument");
+  NVD_REQUIRE(cfg->mode == NVD_MC_STAGED, "the host-buffer step runs the staged pipeline (info words come from the host)");
+  McBuffers b;
+  NVD_TRY(carve_mc(ctx, cfg->L, cfg->y_dtype, static_cast<int64_t>(cfg->frames), &b));
+  const float sigma = sigma_of_db(snr_db);
+  NVD_CUDA(cudaMemsetAsync(ctx->counters_scratch, 0, 4 * sizeof(uint64_t), ctx->stream));
+  for (uint64_t done = 0; done < cfg->frames; done += b.chunk) {
+    const int64_t n = static_cast<int64_t>(std::min<uint64_t>(b.chunk, cfg->frames - done));
+    NVD_CUDA(cudaMemcpyAsync(b.info, info_host + done, static_cast<size_t>(n), cudaMemcpyHostToDevice, ctx->stream));
+    NVD_TRY(staged_chunk(ctx, cfg, m, b, sigma, snr_idx, cfg->frame0 + done, n, true, ctx->counters_scratch, false));
+    if (pred_host) NVD_CUDA(cudaMemcpyAsync(pred_host + done, b.pred, static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+    if (done + b.chunk < cfg->frames) NVD_CUDA(cudaStreamSynchronize(ctx->stream));  // buffers are reused
+  }
+  NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NVD_TRY(nvd_sync(ctx));
+  for (int i = 0; i < 4; ++i) counters_host[i] = ctx->counters_pinned[i];
+  return NVD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// common.cuh — context object, error plumbing and launch declarations shared by libnvd's
+// translation units.  Nothing here is visible through the C ABI (include/nvd.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nvd.h"
+
+namespace nvd {
+
+void set_error(const char* fmt, ...);
+
+#define NVD_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::nvd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,     \
+                       __LINE__);                                                            \
+      return _e == cudaErrorMemoryAllocation ? NVD_ERR_OOM : NVD_ERR_CUDA;                   \
+    }                                                                                        \
+  } while (0)
+
+#define NVD_CHECK_LAUNCH() NVD_CUDA(cudaGetLastError())
+
+#define NVD_REQUIRE(cond, ...)                                                               \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ::nvd::set_error(__VA_ARGS__);                                                         \
+      return NVD_ERR_INVALID;                                                                \
+    }                                                                                        \
+  } while (0)
+
+#define NVD_TRY(expr)                                                                        \
+  do {                                                                                       \
+    int _s = (expr);                                                                         \
+    if (_s != NVD_OK) return _s;                                                             \
+  } while (0)
+
+constexpr int kMaxLayers = 8;
+
+// A loaded feed-forward decoder (weights resident in HBM for the context's lifetime).
+struct MlpModel {
+  bool live = false;
+  int n_layers = 0;
+  int dims[kMaxLayers + 1] = {0};
+  int acts[kMaxLayers] = {0};
+  float* W[kMaxLayers] = {nullptr};  // fp32 [in, out] row-major
+  float* b[kMaxLayers] = {nullptr};
+  // tensor-core image: bf16 weights pre-arranged in the UMMA canonical K-major layout with the
+  // bias rows folded in (k3_mlp_tc.cu); nullptr when the shape is not covered.
+  void* tc_image = nullptr;
+  size_t tc_image_bytes = 0;
+  float* tc_bias_out = nullptr;  // reserved
+};
+
+struct LstmModel {
+  bool live = false;
+  int H = 0;
+  float* blob = nullptr;  // [enc Wp | enc b | dec Wp | dec b | lin_w | lin_b], gate-interleaved
+  size_t blob_floats = 0;
+};
+
+}  // namespace nvd
+
+struct nvd_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<nvd::MlpModel> mlps;
+  std::vector<nvd::LstmModel> lstms;
+  // device-side abort flag written by kernels whose bounded waits expire
+  int* abort_flag = nullptr;       // device
+  int* abort_flag_host = nullptr;  // pinned mirror
+  // scratch owned by the context (grown on demand)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* mc_buf = nullptr;                // staged Monte-Carlo buffers (info | coded | y | pred)
+  size_t mc_buf_bytes = 0;
+  void* pin_buf = nullptr;               // reserved pinned staging
+  uint64_t* counters_scratch = nullptr;  // device uint64[4]
+  uint64_t* counters_pinned = nullptr;   // pinned uint64[4]
+  // staged-pipeline stage timing
+  cudaEvent_t stage_ev[6] = {nullptr};
+  float stage_ms[5] = {0, 0, 0, 0, 0};
+  bool stage_timing = false;
+};
+
+namespace nvd {
+
+int ensure_scratch(nvd_ctx* ctx, size_t bytes);
+
+// ---- kernel launchers (each validates nothing; the API layer does) -----------------------
+int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed);
+int launch_encode(nvd_ctx* ctx, int code, const uint8_t* info, int L, int64_t B, uint8_t* coded);
+int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float sigma, int snr_idx,
+                   uint64_t frame0, int out_dtype, void* y);
+int launch_mlp_fp32(nvd_ctx* ctx, const MlpModel& m, const void* y, int y_dtype, int64_t B,
+                    float* soft_out, void* hard_out, int hard_bytes);
+int launch_count(nvd_ctx* ctx, const void* pred, const void* label, int stride, int L, int64_t B,
+                 int flags, uint64_t* counters);
+int launch_lstm(nvd_ctx* ctx, const LstmModel& m, const void* y, int y_dtype, const float* dec_in,
+                int T_enc, int T_dec, int64_t B, int fast_math, float* logits, uint8_t* hard);
+
+// tensor-core path (k3_mlp_tc.cu)
+bool tc_shape_supported(const MlpModel& m);
+int tc_build_image(nvd_ctx* ctx, MlpModel& m, const float* const* W_host, const float* const* b_host);
+// staged: y bf16 [B, 14] -> soft/hard
+int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y, int64_t B,
+                         float* soft_out, void* hard_out, int hard_bytes);
+// fused: frames [frame0, frame0+frames) generated on chip, counters accumulated
+int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float sigma, int snr_idx,
+                        uint64_t frame0, uint64_t frames, uint64_t* counters);
+
+}  // namespace nvd

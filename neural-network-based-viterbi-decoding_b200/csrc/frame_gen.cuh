@@ -1,0 +1,101 @@
+// frame_gen.cuh — device functions shared by the staged kernels (K0/K1/K2) and the fused
+// pipeline kernel, so that both produce bit-identical frames:
+//   * Philox4x32-10 counter-based generator (checked word-for-word against oracle/philox.py)
+//   * Box–Muller on MUFU (lg2 / sqrt / sin / cos approximations)
+//   * shift-XOR convolutional encoder on time-packed words
+//       encode_133171  /root/reference/src/fnn_viterbi.py:157-217  taps {0,2,3,5,6} / {0,1,2,3,6}
+//       encode_57      /root/reference/src/fnn_viterbi.py:122-154  taps {0,2} / {0,1,2}, g=5 first,
+//                      plus the non-causal c[1] = b0^b1 of :143
+//   * class label <-> time-packed word (generate_class_bits is MSB-first, fnn_viterbi.py:283)
+#pragma once
+
+#include <cstdint>
+
+namespace nvd {
+
+constexpr uint32_t kStreamNoise = 1u;
+constexpr uint32_t kStreamInfo = 2u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c.x;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c.z;
+    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ k0, static_cast<uint32_t>(p1),
+                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ k1, static_cast<uint32_t>(p0));
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// counter convention (oracle/philox.py): (frame_lo, frame_hi, block, (snr_idx << 8) | stream)
+__device__ __forceinline__ uint4 frame_words(uint64_t seed, uint64_t frame, uint32_t block,
+                                             uint32_t stream_word) {
+  return philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32),
+                                  block, stream_word),
+                       static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+
+__host__ __device__ __forceinline__ uint32_t noise_stream_word(int snr_idx) {
+  return (static_cast<uint32_t>(snr_idx) << 8) | kStreamNoise;
+}
+
+// two 32-bit words -> two N(0,1) draws (float64 statement: oracle/philox.py box_muller)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float th = __int2float_rn(static_cast<int>(b)) * 1.4629180792671596e-9f;  // pi * 2^-31
+  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));                     // sqrt(-2 ln u1)
+  float s, c;
+  __sincosf(th, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// 4 standard normals of symbols 4*block .. 4*block+3 of `frame`
+__device__ __forceinline__ void noise4(uint64_t seed, uint64_t frame, uint32_t block,
+                                       uint32_t stream_word, float z[4]) {
+  const uint4 x = frame_words(seed, frame, block, stream_word);
+  box_muller(x.x, x.y, z[0], z[1]);
+  box_muller(x.z, x.w, z[2], z[3]);
+}
+
+// ---- encoder on packed words ---------------------------------------------------------------
+// v = (u << 6) | hist6, hist6 bit 5 = info bit at time -1 ... bit 0 = time -6.
+// Returns generator outputs for the (up to 32) time steps held in u.
+__device__ __forceinline__ void conv_outputs(uint64_t v, int code, uint32_t& oa, uint32_t& ob) {
+  if (code == NVD_CODE_133171) {
+    oa = static_cast<uint32_t>((v >> 6) ^ (v >> 4) ^ (v >> 3) ^ (v >> 1) ^ v);
+    ob = static_cast<uint32_t>((v >> 6) ^ (v >> 5) ^ (v >> 4) ^ (v >> 3) ^ v);
+  } else {
+    oa = static_cast<uint32_t>((v >> 6) ^ (v >> 4));
+    ob = static_cast<uint32_t>((v >> 6) ^ (v >> 5) ^ (v >> 4));
+  }
+}
+
+// spread the low 16 bits of x to the even bit positions
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+// coded bits (interleaved [g_a(i), g_b(i)]) of `nvalid` (<= 16) info bits `u` (already masked
+// to its valid bits) with history hist6; frame_start applies the (7,5) reference quirk.  Bits
+// at and above 2*nvalid are returned zero.
+__device__ __forceinline__ uint32_t encode16(uint32_t u, uint32_t hist6, int code, bool frame_start,
+                                             int nvalid) {
+  uint32_t oa, ob;
+  conv_outputs((static_cast<uint64_t>(u) << 6) | hist6, code, oa, ob);
+  if (code == NVD_CODE_57_REF && frame_start) ob ^= (u >> 1) & 1u;
+  const uint32_t w = spread16(oa) | (spread16(ob) << 1);
+  return nvalid >= 16 ? w : (w & ((1u << (2 * nvalid)) - 1u));
+}
+
+// MSB-first class index <-> time-packed word (bit reversal over L bits, L <= 32)
+__device__ __forceinline__ uint32_t bitrev_L(uint32_t x, int L) { return __brev(x) >> (32 - L); }
+
+}  // namespace nvd

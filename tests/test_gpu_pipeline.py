@@ -1,0 +1,103 @@
+"""GPU tests of the whole Monte-Carlo step (encode -> channel -> decode -> count) through the C ABI:
+fused == staged, shard invariance, oracle parity of the counters, host-buffer (end-to-end) form,
+and size-independent properties at BASELINE.json's full size (2^24 frames / SNR point)."""
+import numpy as np
+import pytest
+
+from oracle import encoders as oenc, mlp as omlp, pipeline as opipe
+
+pytestmark = pytest.mark.gpu
+SEED = 20170710
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from nvd import montecarlo
+    with montecarlo.Simulator(device=0, seed=SEED) as s:
+        yield s
+
+
+@pytest.fixture(scope="module")
+def model():
+    from nvd import weights
+    return weights.load_default_fnn()
+
+
+@pytest.fixture(scope="module")
+def handle(sim, model):
+    return sim.load_mlp(model)
+
+
+@pytest.mark.parametrize("frames,frame0", [(1, 0), (127, 5), (128, 0), (1000, 123), (65536 + 77, 1 << 33)])
+def test_fused_equals_staged(sim, handle, frames, frame0):
+    snr = [0.0, 3.0, 6.0]
+    fused = sim.run(handle, "133171", 7, snr, frames, frame0, mode="fused")
+    staged = sim.run(handle, "133171", 7, snr, frames, frame0, mode="staged", precision="bf16")
+    assert (fused == staged).all()                      # bit-identical frames and arithmetic
+    assert (fused[:, 2] == frames).all() and (fused[:, 3] == frames * 7).all()
+    assert (fused[:, 1] <= frames).all() and (fused[:, 0] >= fused[:, 1]).all()
+
+
+def test_shard_invariance(sim, handle):
+    """Counters for N frames are identical for any split into rank ranges."""
+    from nvd.montecarlo import shard_range
+    N, snr = 100000, [1.0, 4.0]
+    whole = sim.run(handle, "133171", 7, snr, N, 42, mode="fused")
+    for world in (2, 3, 8):
+        acc = np.zeros_like(whole)
+        for rank in range(world):
+            lo, n = shard_range(42, N, rank, world)
+            acc += sim.run(handle, "133171", 7, snr, n, lo, mode="fused")
+        assert (acc == whole).all()
+    via_rank_api = sum(sim.run(handle, "133171", 7, snr, N, 42, mode="fused", rank=r, world=4) for r in range(4))
+    assert (via_rank_api == whole).all()
+
+
+@pytest.mark.parametrize("code,name", [(oenc.CODE_133171, "133171"), (oenc.CODE_57_REF, "57")])
+def test_counters_match_oracle(sim, handle, model, code, name):
+    """Same frames (Philox) through the CPU oracle: fp32 CUDA path must agree up to near-tie frames,
+    bf16 tensor-core path up to the frames whose top-2 margin is inside the bf16 tolerance."""
+    frames, snr_db = 1 << 15, 2.0
+    ref, det = opipe.mc_step(model.Ws, model.bs, model.acts, 7, code, snr_db, 0, frames, seed=SEED, snr_idx=0,
+                             noise="philox", precision="fp64", return_detail=True)
+    margin = omlp.top2_margin(det["out"])
+    fp32 = sim.run(handle, name, 7, [snr_db], frames, 0, mode="staged", precision="fp32", y_dtype="f32")[0]
+    assert abs(int(fp32[1]) - int(ref[1])) <= int((margin < 1e-3).sum())
+    assert abs(int(fp32[0]) - int(ref[0])) <= 7 * int((margin < 1e-3).sum())
+    tc = sim.run(handle, name, 7, [snr_db], frames, 0, mode="fused")[0]
+    assert abs(int(tc[1]) - int(ref[1])) <= int((margin < 5e-2).sum())
+    assert tc[2] == ref[2] and tc[3] == ref[3]
+
+
+def test_host_buffer_step_matches_device_step(sim, handle):
+    frames = 50000
+    info = oenc.class_to_packed(np.arange(frames) & 127, 7).astype(np.uint8)
+    pred = np.zeros(frames, np.uint8)
+    c_host = sim.run_host(handle, "133171", 7, 3.0, info, pred, frame0=0, precision="bf16", snr_idx=0)
+    c_dev = sim.run(handle, "133171", 7, [3.0], frames, 0, mode="staged", precision="bf16")[0]
+    assert (c_host == c_dev).all()
+    errs = np.array([bin(int(a) ^ int(b)).count("1") for a, b in zip(pred[:5000], np.arange(5000) & 127)])
+    assert errs.sum() <= c_host[0]
+
+
+def test_full_size_properties(sim, handle):
+    """BASELINE.json configs[1] size: 2^24 frames per SNR point.  Size-independent checks: totals,
+    monotone BER in SNR, fused == sum of two half ranges, noiseless channel decodes the code book."""
+    N = 1 << 24
+    snr = [0.0, 4.0, 8.0]
+    c = sim.run(handle, "133171", 7, snr, N, 0, mode="fused")
+    assert (c[:, 2] == N).all() and (c[:, 3] == 7 * N).all()
+    ber = c[:, 0] / c[:, 3]
+    assert ber[0] > ber[1] > ber[2]
+    halves = sim.run(handle, "133171", 7, snr, N // 2, 0, mode="fused") + sim.run(handle, "133171", 7, snr, N // 2, N // 2, mode="fused")
+    assert (halves == c).all()
+
+
+def test_bad_arguments_fail_loudly(sim, handle):
+    from nvd import NvdError
+    with pytest.raises(NvdError):
+        sim.run(handle, "133171", 9, [1.0], 10)              # L does not match the model
+    with pytest.raises(NvdError):
+        sim.run(99, "133171", 7, [1.0], 10)                  # bad handle
+    with pytest.raises(NvdError):
+        sim.run(handle, "133171", 7, [1.0], 10, mode="fused", precision="fp32")
