@@ -180,6 +180,9 @@ int nvd_mc_set_stage_timing(nvd_ctx* ctx, int enabled);
  * and descriptor strides; used by tests/test_gpu_umma_probe.py to pin the UMMA shared-memory
  * layout the tensor-core kernel relies on.  a_image_host: 4096 B, b_image_host: N*32 B,
  * d_host: [128, N] fp32. */
+/* phase time stamps (clock64) of CTA 0's four groups over their first 64 tiles of a fused run:
+ * stamps_host[(tile * 4 + group) * 16 + phase]. */
+int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uint64_t* stamps_host);
 int nvd_debug_umma_probe(nvd_ctx* ctx, int N, int a_lbo_bytes, int a_sbo_bytes, int b_lbo_bytes,
                          int b_sbo_bytes, const void* a_image_host, const void* b_image_host,
                          float* d_host);

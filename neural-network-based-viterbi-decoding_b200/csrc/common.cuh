@@ -59,6 +59,7 @@ struct MlpModel {
   void* tc_image = nullptr;
   size_t tc_image_bytes = 0;
   float* tc_bias_out = nullptr;  // reserved
+  float tc_out_offset = 0.0f;    // power of two added to the output accumulators (positive-key argmax)
 };
 
 struct LstmModel {

@@ -19,12 +19,14 @@ constexpr uint32_t kStreamInfo = 2u;
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
+    // round keys as key + r * Weyl constant: with a warp-uniform key (kernel parameter) they are
+    // computed once in the uniform datapath instead of 20 vector adds per call
+    const uint32_t rk0 = k0 + static_cast<uint32_t>(r) * 0x9E3779B9u;
+    const uint32_t rk1 = k1 + static_cast<uint32_t>(r) * 0xBB67AE85u;
     const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c.x;
     const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c.z;
-    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ k0, static_cast<uint32_t>(p1),
-                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ k1, static_cast<uint32_t>(p0));
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ rk0, static_cast<uint32_t>(p1),
+                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ rk1, static_cast<uint32_t>(p0));
   }
   return c;
 }
@@ -41,15 +43,20 @@ __host__ __device__ __forceinline__ uint32_t noise_stream_word(int snr_idx) {
   return (static_cast<uint32_t>(snr_idx) << 8) | kStreamNoise;
 }
 
-// two 32-bit words -> two N(0,1) draws (float64 statement: oracle/philox.py box_muller)
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// two 32-bit words -> two N(0,1) draws (float64 statement: oracle/philox.py box_muller); four MUFU
+// operations per pair: lg2, sqrt, sin, cos
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float th = __int2float_rn(static_cast<int>(b)) * 1.4629180792671596e-9f;  // pi * 2^-31
-  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));                     // sqrt(-2 ln u1)
-  float s, c;
-  __sincosf(th, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
+  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u1));               // sqrt(-2 ln u1)
+  z0 = r * __cosf(th);
+  z1 = r * __sinf(th);
 }
 
 // 4 standard normals of symbols 4*block .. 4*block+3 of `frame`
@@ -58,6 +65,30 @@ __device__ __forceinline__ void noise4(uint64_t seed, uint64_t frame, uint32_t b
   const uint4 x = frame_words(seed, frame, block, stream_word);
   box_muller(x.x, x.y, z[0], z[1]);
   box_muller(x.z, x.w, z[2], z[3]);
+}
+
+// 8 standard normals of symbols 4*block .. 4*block+7: the same arithmetic as two noise4 calls, written
+// stage by stage (both Philox chains, then all lg2, all sqrt, all sin/cos) so that the MUFU
+// operations of the four Box-Muller pairs are in flight together instead of queueing one by one.
+__device__ __forceinline__ void noise8(uint64_t seed, uint64_t frame, uint32_t block,
+                                       uint32_t stream_word, float z[8]) {
+  const uint4 x0 = frame_words(seed, frame, block, stream_word);
+  const uint4 x1 = frame_words(seed, frame, block + 1, stream_word);
+  const uint32_t a[4] = {x0.x, x0.z, x1.x, x1.z};
+  const uint32_t b[4] = {x0.y, x0.w, x1.y, x1.w};
+  float l[4], th[4], r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    l[i] = __log2f(fmaf(__uint2float_rn(a[i]), 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+    th[i] = __int2float_rn(static_cast<int>(b[i])) * 1.4629180792671596e-9f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    z[2 * i] = r[i] * __cosf(th[i]);
+    z[2 * i + 1] = r[i] * __sinf(th[i]);
+  }
 }
 
 // ---- encoder on packed words ---------------------------------------------------------------

@@ -46,20 +46,21 @@ static_assert(W_BYTES == 39936, "weight image size");
 // shared memory carve-up
 constexpr int ONES_OFF = W_BYTES;                     // [128 x 16] A chunk, column 0 = 1.0
 constexpr int GROUP_OFF = ONES_OFF + 4096;
-constexpr int A1_OFF = 0;                             // [128 x 16]
-constexpr int A2_OFF = 4096;                          // [128 x 128]; A3 / A4 alias into it
+constexpr int A1_OFF = 0;                             // 2 x [128 x 16] (double-buffered by the producer warp)
+constexpr int A2_OFF = 8192;                          // [128 x 128]; A3 / A4 alias into it
 constexpr int A3_OFF = A2_OFF;
 constexpr int A4_OFF = A2_OFF + 16384;
 constexpr int YBUF_OFF = A2_OFF + 32768;              // 128 x 28 B TMA landing buffer
 constexpr int GROUP_BYTES = YBUF_OFF + 128 * kRowBytes;
 constexpr int BAR_OFF = GROUP_OFF + kGroups * GROUP_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + 128;
+constexpr int SMEM_BYTES = BAR_OFF + 256;
+constexpr int kThreadsFused = kThreads + 32 * kGroups;  // + one frame-producer warp per group
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(GROUP_BYTES % 128 == 0 && GROUP_OFF % 128 == 0, "alignment");
 
 constexpr int A_LBO = 128 * 16;  // bytes between the two K chunks of an A operand (128 rows)
 constexpr int kSBO = 128;        // bytes between 8-row groups
-constexpr uint32_t kMaxTries = 1u << 20;
+constexpr uint32_t kMaxWaitMs = 2000;  // bounded mbarrier waits (wall clock)
 
 enum { MODE_STAGED = 0, MODE_FUSED = 1 };
 
@@ -73,6 +74,8 @@ struct TcParams {
   void* hard;
   int hard_bytes;
   int last_act;
+  float out_offset;  // constant added to every output accumulator by the last MMA step
+  uint64_t* timing;  // diagnostics: phase time stamps (nullptr = off)
   int use_tma;
   // fused
   uint64_t seed;
@@ -97,49 +100,111 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
   return v;
 }
 
-// hidden-layer epilogue: TMEM accumulator (bias already inside) -> tanh -> bf16 -> next A operand
-template <int N>
+// hidden-layer epilogue over columns [C0, C1): TMEM accumulator (bias already inside) -> tanh ->
+// bf16 -> next layer's A operand (canonical layout: 16-byte K chunk q of row r at q*A_LBO + r*16)
+__device__ __forceinline__ void tanh_pack_store32(const uint32_t (&v)[32], uint32_t a_next, int c, int r) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#ifdef NVD_EXP_NO_TANH
+      w[e] = pack_bf16x2(__uint_as_float(v[8 * q + 2 * e]) * 0.125f, __uint_as_float(v[8 * q + 2 * e + 1]) * 0.125f);
+#else
+      w[e] = pack_bf16x2(ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e])),
+                         ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e + 1])));
+#endif
+    st_shared_v4(a_next + ((c >> 3) + q) * A_LBO + r * 16, w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int C0, int C1>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint32_t a_next, int r) {
+  if constexpr ((C1 - C0) % 64 == 0) {
+    // two TMEM loads in flight per wait: halves the exposed tcgen05.ld latency
 #pragma unroll
-  for (int c = 0; c < N; c += 32) {
-    uint32_t v[32];
-    ptx::tmem_ld32(tmem_d + c, v);
-    ptx::tmem_wait_ld();
+    for (int c = C0; c < C1; c += 64) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(tmem_d + c, v0);
+      ptx::tmem_ld32(tmem_d + c + 32, v1);
+      ptx::tmem_wait_ld();
+      tanh_pack_store32(v0, a_next, c, r);
+      tanh_pack_store32(v1, a_next, c + 32, r);
+    }
+  } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        w[e] = pack_bf16x2(ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e])),
-                           ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e + 1])));
-      st_shared_v4(a_next + ((c >> 3) + q) * A_LBO + r * 16, w[0], w[1], w[2], w[3]);
+    for (int c = C0; c < C1; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_d + c, v);
+      ptx::tmem_wait_ld();
+      tanh_pack_store32(v, a_next, c, r);
     }
   }
 }
 
+// one frame: info word -> encoder -> BPSK + Philox AWGN -> 14 bf16 symbols (+ the 1.0 bias column) as
+// the 8 packed words of its A1 row.  Same device functions as K0/K1/K2 => bit-identical frames.
+__device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_t lmask, uint32_t (&w)[8]) {
+  const uint32_t cls = static_cast<uint32_t>(f) & lmask;
+  const uint32_t coded = encode16(bitrev_L(cls, p.L), 0u, p.code, true, p.L);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float z[8];
+    noise8(p.seed, f, 2 * half, p.stream_word, z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = 8 * half + 2 * i;
+      w[4 * half + i] = pack_bf16x2(fmaf(p.sigma, z[2 * i], ((coded >> j) & 1u) ? 1.0f : -1.0f),
+                                    fmaf(p.sigma, z[2 * i + 1], ((coded >> (j + 1)) & 1u) ? 1.0f : -1.0f));
+    }
+  }
+  w[7] = 0x00003F80u;  // (1.0, 0.0): bias column 14, zero column 15
+}
+
+// synchronise the group's 128 threads around a hand-off to the tensor core (async proxy)
+__device__ __forceinline__ void group_handoff(int g) {
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  ptx::bar_sync(1 + g, 128);
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   const int tid = threadIdx.x;
-  const int g = tid >> 7;
+  // warp-uniform indices come from a shuffle so that ptxas keeps everything derived from them
+  // (shared-memory / TMEM addresses, UMMA descriptors) in uniform registers: without it every
+  // tcgen05.mma / tcgen05.ld is wrapped in an ELECT + R2UR.BROADCAST "waterfall" loop.
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  const bool is_producer = (MODE == MODE_FUSED) && warp >= kThreads / 32;   // warps 16..19, one per group
+  const int g = is_producer ? (warp - kThreads / 32) : (warp >> 2);
+  const int wq = warp & 3;                                                // warp within its group
+  const bool issuer_warp = !is_producer && wq == 0;                       // issues this group's MMAs / TMA
   const int r = tid & 127;
   const uint32_t grp = sbase + GROUP_OFF + g * GROUP_BYTES;
   const uint32_t bar_mma = sbase + BAR_OFF + 8 * g;
   const uint32_t bar_tma = sbase + BAR_OFF + 32 + 8 * g;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 64);
+  const uint32_t bar_full = sbase + BAR_OFF + 64 + 16 * g;    // [2] per group: A1[buf] produced
+  const uint32_t bar_empty = sbase + BAR_OFF + 128 + 16 * g;  // [2] per group: A1[buf] consumed by MMA1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 192);
 
   // ---- one-time set-up: weights -> smem, ones chunk, barriers, TMEM --------------------------
-  for (int i = tid; i < W_BYTES / 16; i += kThreads)
+  for (int i = tid; i < W_BYTES / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(p.image) + i);
-  for (int i = tid; i < 4096 / 16; i += kThreads) {
-    // chunk 0 (columns 0..7) rows 0..127: column 0 = bf16(1.0) = 0x3F80; chunk 1 all zero
-    reinterpret_cast<uint4*>(smem + ONES_OFF)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 4096 / 16; i += blockDim.x) {
+    // chunk 0 (columns 0..7) rows 0..127: columns 0 and 1 = bf16(1.0) = 0x3F80 (column 0 meets the
+    // bias row of B, column 1 the output-offset row, which is zero for layers 2 and 3); chunk 1 zero
+    reinterpret_cast<uint4*>(smem + ONES_OFF)[i] = (i < 128) ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid == 0) {
     for (int i = 0; i < kGroups; ++i) {
       ptx::mbar_init(sbase + BAR_OFF + 8 * i, 1);
       ptx::mbar_init(sbase + BAR_OFF + 32 + 8 * i, 1);
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(sbase + BAR_OFF + 64 + 16 * i + 8 * b, 1);
+        ptx::mbar_init(sbase + BAR_OFF + 128 + 16 * i + 8 * b, 1);
+      }
     }
     ptx::mbar_fence_init();
   }
@@ -151,9 +216,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
   const uint32_t tmem_grp = tmem_base + g * 128;                         // MMA destination (lane 0)
-  const uint32_t tmem_d = tmem_grp + (static_cast<uint32_t>(r & ~31) << 16);  // this warp's lanes
+  const uint32_t tmem_d = tmem_grp + (static_cast<uint32_t>(wq * 32) << 16);  // this warp's lanes
 
   constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(128, 128);
   constexpr uint32_t idesc64 = ptx::make_idesc_bf16_f32(128, 64);
@@ -167,19 +232,63 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
   const uint32_t lmask = (1u << p.L) - 1u;
 
   auto tile_uses_tma = [&](int64_t t) { return p.use_tma && (t + 1) * 128 <= p.B; };
-  if (MODE == MODE_STAGED && r == 0 && tile < num_tiles && tile_uses_tma(tile)) {
+  if (MODE == MODE_STAGED && issuer_warp && tile < num_tiles && tile_uses_tma(tile) && ptx::elect_one()) {
     ptx::mbar_arrive_expect_tx(bar_tma, 128 * kRowBytes);
     ptx::bulk_g2s(grp + YBUF_OFF, reinterpret_cast<const uint8_t*>(p.y) + tile * 128 * kRowBytes, 128 * kRowBytes, bar_tma);
   }
 
-  for (; tile < num_tiles; tile += tile_stride) {
+  // ---- fused mode, producer warps: warp 16+g generates the frames of group g's tiles, one tile ahead
+  //      (two A1 buffers), so frame generation (Philox chains, Box-Muller's serial MUFU stages) never
+  //      sits on the consumers' critical path.  full/empty mbarriers hand the buffers back and forth.
+  if (is_producer) {
+    const int lane = tid & 31;
+    int it = 0;
+    for (; tile < num_tiles; tile += tile_stride, ++it) {
+      const int buf = it & 1;
+      if (!ptx::mbar_wait_bounded(bar_empty + 8 * buf, ((it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 6); break; }
+      const uint32_t a1 = grp + A1_OFF + buf * 4096;
+#pragma unroll 1
+      for (int q = 0; q < 4; q += 2) {  // two frames per lane in flight: 4 Philox chains, 8 Box-Muller pairs
+        const int r0 = 32 * q + lane, r1 = r0 + 32;
+        uint32_t w0[8], w1[8];
+#ifdef NVD_EXP_NO_GEN
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { w0[i] = 0x3F003F00u + r0; w1[i] = 0xBF003F00u + r1; }
+#else
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(tile * 128 + r0), lmask, w0);
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(tile * 128 + r1), lmask, w1);
+#endif
+        st_shared_v4(a1 + r0 * 16, w0[0], w0[1], w0[2], w0[3]);
+        st_shared_v4(a1 + A_LBO + r0 * 16, w0[4], w0[5], w0[6], w0[7]);
+        st_shared_v4(a1 + r1 * 16, w1[0], w1[1], w1[2], w1[3]);
+        st_shared_v4(a1 + A_LBO + r1 * 16, w1[4], w1[5], w1[6], w1[7]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_full + 8 * buf);
+    }
+  }
+
+  // optional phase timing (diagnostics): thread 0 of every group of CTA 0 stamps clock64 at the
+  // phase boundaries of its first 64 tiles into p.timing[(tile_local * 4 + g) * 16 + i]
+  int tile_local = 0;
+#define NVD_STAMP(i)                                                                      \
+  do {                                                                                    \
+    if (p.timing != nullptr && blockIdx.x == 0 && r == 0 && tile_local < 64)             \
+      p.timing[(tile_local * kGroups + g) * 16 + (i)] = static_cast<uint64_t>(clock64()); \
+  } while (0)
+
+  for (; !is_producer && tile < num_tiles; tile += tile_stride, ++tile_local) {
     const int64_t row = tile * 128 + r;
+    NVD_STAMP(0);
     uint32_t cls = 0;
-    // ---- stage 0: this frame's 14 noisy symbols -> A1 (K padded to 16, column 14 = 1.0) -------
-    uint32_t w[8];
+    const int buf = (MODE == MODE_FUSED) ? (tile_local & 1) : 0;
+    // ---- stage 0: A1 (K padded to 16, column 14 = 1.0).  Staged: this frame's 14 symbols come from
+    //      HBM (TMA landing buffer); fused: the producer warp has written the whole tile.
     if (MODE == MODE_STAGED) {
+      uint32_t w[8];
       if (tile_uses_tma(tile)) {
-        if (!ptx::mbar_wait_bounded(bar_tma, tma_phase, kMaxTries)) { atomicExch(p.abort_flag, 1); break; }
+        if (!ptx::mbar_wait_bounded(bar_tma, tma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 1); break; }
         tma_phase ^= 1;
 #pragma unroll
         for (int i = 0; i < 7; ++i) w[i] = ld_shared_u32(grp + YBUF_OFF + r * kRowBytes + 4 * i);
@@ -188,33 +297,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) w[i] = (row < p.B) ? __ldg(src + i) : 0u;
       }
+      w[7] = 0x00003F80u;
+      st_shared_v4(grp + A1_OFF + r * 16, w[0], w[1], w[2], w[3]);
+      st_shared_v4(grp + A1_OFF + A_LBO + r * 16, w[4], w[5], w[6], w[7]);
+      group_handoff(g);
     } else {
-      const uint64_t f = p.frame0 + static_cast<uint64_t>(row);
-      cls = static_cast<uint32_t>(f) & lmask;
-      const uint32_t coded = encode16(bitrev_L(cls, p.L), 0u, p.code, true, p.L);
-      float yv[16];
-#pragma unroll
-      for (int blk = 0; blk < 4; ++blk) {
-        float z[4];
-        noise4(p.seed, f, blk, p.stream_word, z);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = 4 * blk + k;
-          yv[j] = fmaf(p.sigma, z[k], ((coded >> j) & 1u) ? 1.0f : -1.0f);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 7; ++i) w[i] = pack_bf16x2(yv[2 * i], yv[2 * i + 1]);
+      cls = static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(row)) & lmask;
+      if (!ptx::mbar_wait_bounded(bar_full + 8 * buf, (tile_local >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 7); break; }
     }
-    w[7] = 0x00003F80u;  // (1.0, 0.0): bias column 14, zero column 15
-    st_shared_v4(grp + A1_OFF + r * 16, w[0], w[1], w[2], w[3]);
-    st_shared_v4(grp + A1_OFF + A_LBO + r * 16, w[4], w[5], w[6], w[7]);
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::bar_sync(1 + g, 128);
+    NVD_STAMP(1);
 
     // ---- layer 1: [128 x 16] x [16 x 128] --------------------------------------------------
-    if (r == 0) {
+    if (issuer_warp && ptx::elect_one()) {
       if (MODE == MODE_STAGED) {
         const int64_t nt = tile + tile_stride;
         if (nt < num_tiles && tile_uses_tma(nt)) {
@@ -223,39 +317,54 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
         }
       }
       ptx::tc_fence_after();
-      ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A1_OFF, A_LBO, kSBO),
+      ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A1_OFF + buf * 4096, A_LBO, kSBO),
                        ptx::make_smem_desc(sbase + W1_OFF, N1 * 16, kSBO), idesc128, 0u);
       ptx::umma_commit(bar_mma);
     }
-    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxTries)) { atomicExch(p.abort_flag, 2); break; }
+    NVD_STAMP(2);
+    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 2); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
-    epilogue_hidden<N1>(tmem_d, grp + A2_OFF, r);
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::bar_sync(1 + g, 128);
+    if (MODE == MODE_FUSED && issuer_warp && ptx::elect_one()) ptx::mbar_arrive(bar_empty + 8 * buf);   // MMA1 has consumed A1[buf]
 
-    // ---- layer 2: [128 x 128(+16)] x [.. x 64] ---------------------------------------------
-    if (r == 0) {
+    // ---- layer 2: [128 x 128(+16)] x [.. x 64], issued in two halves as A2 becomes available ----
+    NVD_STAMP(3);
+    epilogue_hidden<0, 64>(tmem_d, grp + A2_OFF, r);
+    NVD_STAMP(4);
+    group_handoff(g);
+    NVD_STAMP(5);
+    if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
 #pragma unroll
-      for (int j = 0; j < N1 / 16; ++j)
+      for (int j = 0; j < 4; ++j)   // D2 overwrites columns 0..63 of D1, which every thread has already read
         ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A2_OFF + j * 2 * A_LBO, A_LBO, kSBO),
                          ptx::make_smem_desc(sbase + W2_OFF + j * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, j > 0);
+    }
+    epilogue_hidden<64, 128>(tmem_d, grp + A2_OFF, r);
+    NVD_STAMP(6);
+    group_handoff(g);
+    NVD_STAMP(7);
+    if (issuer_warp && ptx::elect_one()) {
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int j = 4; j < N1 / 16; ++j)
+        ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A2_OFF + j * 2 * A_LBO, A_LBO, kSBO),
+                         ptx::make_smem_desc(sbase + W2_OFF + j * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, 1u);
       ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
                        ptx::make_smem_desc(sbase + W2_OFF + (N1 / 16) * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, 1u);
       ptx::umma_commit(bar_mma);
     }
-    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxTries)) { atomicExch(p.abort_flag, 3); break; }
+    NVD_STAMP(8);
+    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 3); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
-    epilogue_hidden<N2>(tmem_d, grp + A3_OFF, r);
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::bar_sync(1 + g, 128);
+    NVD_STAMP(9);
+    epilogue_hidden<0, N2>(tmem_d, grp + A3_OFF, r);
+    group_handoff(g);
+    NVD_STAMP(10);
 
     // ---- layer 3: [128 x 64(+16)] x [.. x 32] ----------------------------------------------
-    if (r == 0) {
+    if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
 #pragma unroll
       for (int j = 0; j < N2 / 16; ++j)
@@ -265,16 +374,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
                        ptx::make_smem_desc(sbase + W3_OFF + (N2 / 16) * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 1u);
       ptx::umma_commit(bar_mma);
     }
-    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxTries)) { atomicExch(p.abort_flag, 4); break; }
+    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 4); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
-    epilogue_hidden<N3>(tmem_d, grp + A4_OFF, r);
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::bar_sync(1 + g, 128);
+    NVD_STAMP(11);
+    epilogue_hidden<0, N3>(tmem_d, grp + A4_OFF, r);
+    group_handoff(g);
+    NVD_STAMP(12);
 
     // ---- layer 4: [128 x 32(+16)] x [.. x 128] ---------------------------------------------
-    if (r == 0) {
+    if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
 #pragma unroll
       for (int j = 0; j < N3 / 16; ++j)
@@ -284,36 +393,55 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
                        ptx::make_smem_desc(sbase + W4_OFF + (N3 / 16) * 2 * (N4 * 16), N4 * 16, kSBO), idesc128, 1u);
       ptx::umma_commit(bar_mma);
     }
-    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxTries)) { atomicExch(p.abort_flag, 5); break; }
+    if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 5); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
 
-    // ---- output epilogue: argmax (first index on ties); tanh is monotone so it is elided for
-    //      the decision and applied only when soft outputs are requested -----------------------
-    float best = -INFINITY;
-    int bi = 0;
+    NVD_STAMP(13);
+    // ---- output epilogue: argmax, first index on ties.  tanh is monotone, so the decision is taken
+    //      on the pre-activation.  The last MMA step also added the constant out_offset (a power of
+    //      two above sum|w|+|b|, image builder), so every accumulator is POSITIVE and its fp32 bit
+    //      pattern orders like an integer.  Key = bits with the low 5 mantissa bits replaced by
+    //      (31 - j): one integer max tree per 32 columns finds value and index together and prefers
+    //      the smaller index on equal keys; the four column blocks are merged with a strict compare.
+    //      Resolution: 2^-18 * out_offset (2.4e-4 for offset 64) — far inside the bf16 tolerance.
+    uint32_t best_key = 0u;
+    int best_c = 0;
+    auto scan32 = [&](const uint32_t (&v)[32], int c) {
+      int k[32];
 #pragma unroll
-    for (int c = 0; c < N4; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_d + c, v);
-      ptx::tmem_wait_ld();
+      for (int j = 0; j < 32; ++j) k[j] = static_cast<int>((v[j] & 0xFFFFFFE0u) | static_cast<uint32_t>(31 - j));
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]);
-        if (x > best) { best = x; bi = c + j; }
-      }
+      for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+        for (int j = 0; j < s; ++j) k[j] = max(k[j], k[j + s]);
+      const uint32_t kb = static_cast<uint32_t>(k[0]);
+      if ((kb & 0xFFFFFFE0u) > (best_key & 0xFFFFFFE0u)) { best_key = kb; best_c = c; }
       if (MODE == MODE_STAGED && p.soft != nullptr && row < p.B) {
         float4* dst = reinterpret_cast<float4*>(p.soft + row * N4 + c);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 o;
-          o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-          o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+          o.x = __uint_as_float(v[j]) - p.out_offset; o.y = __uint_as_float(v[j + 1]) - p.out_offset;
+          o.z = __uint_as_float(v[j + 2]) - p.out_offset; o.w = __uint_as_float(v[j + 3]) - p.out_offset;
           if (p.last_act == NVD_ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
           dst[j >> 2] = o;
         }
       }
+    };
+#ifndef NVD_EXP_NO_ARGMAX
+#pragma unroll
+    for (int c = 0; c < N4; c += 64) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(tmem_d + c, v0);
+      ptx::tmem_ld32(tmem_d + c + 32, v1);
+      ptx::tmem_wait_ld();
+      scan32(v0, c);
+      scan32(v1, c + 32);
     }
+#endif
+    const int bi = best_c + 31 - static_cast<int>(best_key & 31u);
+    NVD_STAMP(14);
     ptx::tc_fence_before();  // TMEM reads done before the next tile's MMA (issued after a bar_sync)
     if (MODE == MODE_STAGED) {
       if (p.hard != nullptr && row < p.B) {
@@ -373,7 +501,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, uint32_t a_lb
                      ptx::make_idesc_bf16_f32(128, N), 0u);
     ptx::umma_commit(bar);
   }
-  if (ptx::mbar_wait_bounded(bar, 0, kMaxTries)) {
+  if (ptx::mbar_wait_bounded(bar, 0, kMaxWaitMs)) {
     ptx::tc_fence_after();
     for (int c = 0; c < N; c += 32) {
       uint32_t v[32];
@@ -400,18 +528,35 @@ uint16_t f32_to_bf16_host(float f) {
 // element (n, k) of a [N x Kpad] K-major B operand in the canonical no-swizzle layout
 inline size_t b_off(int N, int n, int k) { return static_cast<size_t>(k >> 3) * (N * 16) + n * 16 + (k & 7) * 2; }
 
-void fill_layer(uint8_t* img, int off, int K, int N, const float* W, const float* b, bool bias_in_pad_col) {
+float bf16_to_f32_host(uint16_t v) {
+  uint32_t u = static_cast<uint32_t>(v) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Returns max_n (sum_k |w_kn| + |b_n|) over the bf16-rounded values: the bound of |x W + b| for |x| <= 1.
+float fill_layer(uint8_t* img, int off, int K, int N, const float* W, const float* b, float extra_col) {
   // W is [K, N] row-major (x @ W); the B operand is W^T.  Bias: at k = K (first column of the pad /
   // of the extra chunk).
+  float bound = 0.0f;
   for (int n = 0; n < N; ++n) {
+    float acc = 0.0f;
     for (int k = 0; k < K; ++k) {
       const uint16_t v = f32_to_bf16_host(W[static_cast<size_t>(k) * N + n]);
       memcpy(img + off + b_off(N, n, k), &v, 2);
+      acc += fabsf(bf16_to_f32_host(v));
     }
     const uint16_t bv = f32_to_bf16_host(b[n]);
     memcpy(img + off + b_off(N, n, K), &bv, 2);
+    acc += fabsf(bf16_to_f32_host(bv));
+    bound = fmaxf(bound, acc);
+    if (extra_col != 0.0f) {  // column K+1 meets the second ones column of the A chunk
+      const uint16_t ev = f32_to_bf16_host(extra_col);
+      memcpy(img + off + b_off(N, n, K + 1), &ev, 2);
+    }
   }
-  (void)bias_in_pad_col;
+  return bound;
 }
 
 template <int MODE>
@@ -420,7 +565,7 @@ int launch_tc(nvd_ctx* ctx, const TcParams& p) {
   NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (p.B + 127) / 128;
   const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, (tiles + kGroups - 1) / kGroups));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(p);
+  kern<<<grid, MODE == MODE_FUSED ? kThreadsFused : kThreads, SMEM_BYTES, ctx->stream>>>(p);
   NVD_CHECK_LAUNCH();
   return NVD_OK;
 }
@@ -439,10 +584,19 @@ bool tc_shape_supported(const MlpModel& m) {
 
 int tc_build_image(nvd_ctx* ctx, MlpModel& m, const float* const* W_host, const float* const* b_host) {
   std::vector<uint8_t> img(W_BYTES, 0);
-  fill_layer(img.data(), W1_OFF, NIN, N1, W_host[0], b_host[0], true);
-  fill_layer(img.data(), W2_OFF, N1, N2, W_host[1], b_host[1], false);
-  fill_layer(img.data(), W3_OFF, N2, N3, W_host[2], b_host[2], false);
-  fill_layer(img.data(), W4_OFF, N3, N4, W_host[3], b_host[3], false);
+  fill_layer(img.data(), W1_OFF, NIN, N1, W_host[0], b_host[0], 0.0f);
+  fill_layer(img.data(), W2_OFF, N1, N2, W_host[1], b_host[1], 0.0f);
+  fill_layer(img.data(), W3_OFF, N2, N3, W_host[2], b_host[2], 0.0f);
+  // output layer: |h3| <= 1, so |z| <= bound; add a power of two above it so every accumulator is positive
+  const float bound = fill_layer(img.data(), W4_OFF, N3, N4, W_host[3], b_host[3], 0.0f);
+  float offset = 1.0f;
+  while (offset <= bound * 1.0625f && offset < 3.0e38f) offset *= 2.0f;
+  if (!(offset <= 4096.0f)) {
+    set_error("output layer bound %g is too large for the tensor-core argmax (max 4096)", bound);
+    return NVD_ERR_UNSUPPORTED;
+  }
+  fill_layer(img.data(), W4_OFF, N3, N4, W_host[3], b_host[3], offset);
+  m.tc_out_offset = offset;
   NVD_CUDA(cudaMalloc(&m.tc_image, W_BYTES));
   NVD_CUDA(cudaMemcpy(m.tc_image, img.data(), W_BYTES, cudaMemcpyHostToDevice));
   m.tc_image_bytes = W_BYTES;
@@ -462,6 +616,7 @@ int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y
   p.hard = hard_out;
   p.hard_bytes = hard_bytes;
   p.last_act = m.acts[3];
+  p.out_offset = m.tc_out_offset;
   p.use_tma = (reinterpret_cast<uintptr_t>(y) % 16 == 0) ? 1 : 0;
   p.L = 7;
   if (reinterpret_cast<uintptr_t>(y) % 4 != 0) { set_error("y must be 4-byte aligned"); return NVD_ERR_INVALID; }
@@ -485,10 +640,43 @@ int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float 
   p.code = code;
   p.L = L;
   p.last_act = m.acts[3];
+  p.out_offset = m.tc_out_offset;
   return launch_tc<MODE_FUSED>(ctx, p);
 }
 
 }  // namespace nvd
+
+extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uint64_t* stamps_host /* [64*4*16] */) {
+  using namespace nvd;
+  NVD_REQUIRE(ctx && stamps_host, "null argument");
+  NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->mlps.size()) && ctx->mlps[model].tc_image, "bad model");
+  NVD_CUDA(cudaSetDevice(ctx->device));
+  const MlpModel& m = ctx->mlps[model];
+  uint64_t* d = nullptr;
+  const size_t bytes = static_cast<size_t>(64) * 4 * 16 * sizeof(uint64_t);
+  NVD_CUDA(cudaMalloc(&d, bytes + 32));
+  NVD_CUDA(cudaMemsetAsync(d, 0, bytes + 32, ctx->stream));
+  TcParams p{};
+  p.image = static_cast<const uint8_t*>(m.tc_image);
+  p.abort_flag = ctx->abort_flag;
+  p.B = static_cast<int64_t>(frames);
+  p.seed = ctx->seed;
+  p.counters = d + 64 * 4 * 16;
+  p.sigma = 0.5f;
+  p.stream_word = noise_stream_word(0);
+  p.code = NVD_CODE_133171;
+  p.L = 7;
+  p.last_act = m.acts[3];
+  p.out_offset = m.tc_out_offset;
+  p.timing = d;
+  int s = launch_tc<MODE_FUSED>(ctx, p);
+  if (s == NVD_OK) {
+    NVD_CUDA(cudaMemcpyAsync(stamps_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    s = nvd_sync(ctx);
+  }
+  cudaFree(d);
+  return s;
+}
 
 extern "C" int nvd_debug_umma_probe(nvd_ctx* ctx, int N, int a_lbo_bytes, int a_sbo_bytes, int b_lbo_bytes,
                                     int b_sbo_bytes, const void* a_image_host, const void* b_image_host, float* d_host) {

@@ -22,6 +22,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -33,11 +36,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a wedged pipeline aborts the kernel instead of hanging the GPU box.
-__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t max_tries) {
-  for (uint32_t i = 0; i < max_tries; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
-  return false;
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Time-bounded wait (max_ms of wall clock): a wedged pipeline aborts the kernel instead of hanging
+// the GPU box.  try_wait itself may suspend the thread for a HW-defined slice, so the bound is on
+// the global timer, not on the number of probes.
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t max_ms) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_timer_ns() - t0 > static_cast<uint64_t>(max_ms) * 1000000ull) return false;
+  }
+  return true;
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------
@@ -50,6 +63,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// one lane of a converged warp (warp-uniform call sites only)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- named barrier over a subset of the CTA ---------------------------------------------------

@@ -8,7 +8,7 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_DIR = os.path.dirname(_HERE)
 ROOT_DIR = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libnvd.so")
+LIB_PATH = os.environ.get("NVD_LIB", os.path.join(PKG_DIR, "libnvd.so"))
 HEADER_PATH = os.path.join(ROOT_DIR, "include", "nvd.h")
 
 # enums of include/nvd.h
@@ -74,6 +74,7 @@ _PROTOS = {
     "nvd_mc_run_host": ([_vp, C.POINTER(McConfig), _f, _i, _vp, _vp, _vp], _i),
     "nvd_mc_stage_ms": ([_vp, C.POINTER(_f)], _i),
     "nvd_mc_set_stage_timing": ([_vp, _i], _i),
+    "nvd_debug_tc_timing": ([_vp, _i, _u64, _vp], _i),
     "nvd_debug_umma_probe": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
 }
 

@@ -1,0 +1,16 @@
+#!/bin/bash
+# build experiment variants of libnvd (only k_mlp_tc.cu recompiled): build/var/libnvd_<VARIANT>.so
+set -e
+cd /root/repo/neural-network-based-viterbi-decoding_b200
+mkdir -p build/var
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+for V in "$@"; do
+  DEFS=""
+  for d in $(echo $V | tr '+' ' '); do DEFS="$DEFS -DNVD_EXP_$d"; done
+  nvcc $FLAGS $DEFS -c csrc/k_mlp_tc.cu -o build/var/k_mlp_tc_$V.o &
+done
+wait
+for V in "$@"; do
+  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/var/libnvd_$V.so build/api.o build/k_source_encode.o build/k_channel.o build/k_mlp_fp32.o build/var/k_mlp_tc_$V.o build/k_lstm.o build/k_count.o
+done
+ls build/var/*.so

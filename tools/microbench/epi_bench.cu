@@ -1,0 +1,82 @@
+// Microbenchmark: the hidden-layer epilogue loop in isolation (tcgen05.ld -> tanh.approx -> bf16 pack ->
+// st.shared.v4) with 16 warps per SM, to find its standalone tanh throughput per SM.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../neural-network-based-viterbi-decoding_b200/csrc -o epi_bench epi_bench.cu
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdint>
+#include "ptx.cuh"
+using namespace nvd;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// VARIANT 0: ld64 + tanh + pack + sts; 1: no LDTM (registers only); 2: no STS; 3: tanh only on regs, no pack
+template <int VARIANT>
+__global__ void __launch_bounds__(512, 1) epi(int iters, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, g = tid >> 7, r = tid & 127;
+  if (tid < 32) { ptx::tmem_alloc(ptx::smem_u32(&slot), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
+  const uint32_t tm = slot + g * 128 + (uint32_t(r & ~31) << 16);
+  const uint32_t a_next = ptx::smem_u32(smem) + g * 32768;
+  float acc = 0.f;
+  uint32_t v0[32], v1[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { v0[j] = __float_as_uint(0.01f * (j + tid)); v1[j] = __float_as_uint(0.02f * (j + tid)); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 128; c += 64) {
+      if (VARIANT != 1 && VARIANT != 3) {
+        ptx::tmem_ld32(tm + c, v0); ptx::tmem_ld32(tm + c + 32, v1); ptx::tmem_wait_ld();
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t* v = h ? v1 : v0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e]));
+            float b = ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e + 1]));
+            if (VARIANT == 3) { w[e] = __float_as_uint(a + b); } else w[e] = pack2(a, b);
+            if (VARIANT == 1 || VARIANT == 3) { v[8 * q + 2 * e] = __float_as_uint(a * 1.01f); v[8 * q + 2 * e + 1] = __float_as_uint(b * 0.99f); }
+          }
+          if (VARIANT == 2 || VARIANT == 3) acc += __uint_as_float(w[0] ^ w[1] ^ w[2] ^ w[3]);
+          else sts4(a_next + (((c + 32 * h) >> 3) + q) * 2048 + r * 16, w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+  ptx::tc_fence_before(); __syncthreads();
+  if (tid < 32) ptx::tmem_dealloc(slot, 512);
+}
+
+template <int V>
+void run(const char* name, int sms) {
+  float* d; cudaMalloc(&d, 4);
+  cudaFuncSetAttribute(epi<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  epi<V><<<sms, 512, 4 * 32768>>>(10, d); cudaDeviceSynchronize();
+  const int iters = 2000;
+  cudaEventRecord(e0); epi<V><<<sms, 512, 4 * 32768>>>(iters, d); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  printf("%-40s %8.3f ms  %6.2f tanh/clk/SM  err=%s\n", name, ms, 512.0 * 128 * iters / (ms * 1e-3) / 1.965e9, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  run<0>("ld64 + tanh + pack + sts.v4", p.multiProcessorCount);
+  run<1>("tanh + pack + sts.v4 (no LDTM)", p.multiProcessorCount);
+  run<2>("ld64 + tanh + pack (no STS)", p.multiProcessorCount);
+  run<3>("tanh only (regs)", p.multiProcessorCount);
+  return 0;
+}
