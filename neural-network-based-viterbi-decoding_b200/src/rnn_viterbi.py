@@ -1,0 +1,172 @@
+"""Drop-in for /root/reference/src/rnn_viterbi.py: LSTM(20) encoder over the 200 noisy symbols,
+LSTM(20) decoder (teacher-forced, as the reference does even at test time), linear 20 -> 1.
+The forward recurrence runs in libnvd's persistent LSTM kernel (weights resident in shared memory,
+state in registers); training (MSE + Adam, off the hot path) is restated with torch autograd.
+
+Reference defects handled: the missing `Optional` import, the
+rank-3 feeds into rank-2 placeholders and the argmax over a size-1 axis (always 0).  Soft output =
+decoder logits; hard decision = logit > 0; `decision='reference'` reproduces the degenerate argmax."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from nvd import runtime, training, weights as _weights
+
+
+class RNNDecoderConfig:
+    """Attribute bag identical to /root/reference/src/rnn_viterbi.py:28-94 (+ `quantize`, `decision`, `fast_math`)."""
+
+    def __init__(self, block_length: int = 100, encoder_hidden_units: int = 20, decoder_hidden_units: Optional[int] = None,
+                 learning_rate: float = 0.01, training_epochs: int = 6, batch_size: int = 100,
+                 beta_regularization: float = 0.001, training_size: int = 100000, test_size: int = 1000,
+                 snr_db_range: Tuple[int, int] = (0, 9), test_snr_index: int = 2, quantize: str = "trunc_int32",
+                 decision: str = "sign", fast_math: bool = False):
+        self.block_length = block_length
+        self.encoded_length = 2 * block_length
+        self.encoder_hidden_units = encoder_hidden_units
+        self.decoder_hidden_units = decoder_hidden_units if decoder_hidden_units else encoder_hidden_units
+        self.vocab_size = 1
+        self.learning_rate = learning_rate
+        self.training_epochs = training_epochs
+        self.batch_size = batch_size
+        self.beta_regularization = beta_regularization
+        self.display_step = 1
+        self.training_size = training_size
+        self.test_size = test_size
+        snr_db_vec = np.arange(snr_db_range[0], snr_db_range[1])
+        self.snr_db_vec = snr_db_vec
+        self.snr_vec = 10 ** (snr_db_vec / 10.0)
+        self.n0_vec = 1.0 / self.snr_vec
+        self.sigma_vec = np.sqrt(self.n0_vec * 0.5)
+        self.test_snr_index = test_snr_index
+        self.PAD = 0
+        self.EOS = 1
+        self.quantize = quantize      # the reference's int32 destination arrays truncate the channel output (:201-208)
+        self.decision = decision      # 'sign' (logit > 0) or 'reference' (argmax over the size-1 axis == 0)
+        self.fast_math = fast_math
+
+
+def encode_133171(bits: np.ndarray) -> np.ndarray:
+    return runtime.get_sim().encode_bits(np.asarray(bits), "133171")
+
+
+def modulate_awgn(encoded_seq: np.ndarray, sigma: float) -> np.ndarray:
+    enc = np.asarray(encoded_seq)
+    rows = enc.reshape(-1, enc.shape[-1])
+    f0 = runtime.take_frames(rows.shape[0])
+    return runtime.get_sim().channel_bits(rows != 0, float(sigma), 0, f0, "f32").astype(np.float64).reshape(enc.shape)
+
+
+def generate_input_vectors(length: int, number: int) -> np.ndarray:
+    return np.random.randint(2, size=(number, length))
+
+
+def _transmit(config: RNNDecoderConfig, info: np.ndarray, sigma: float) -> np.ndarray:
+    sim = runtime.get_sim()
+    coded = sim.encode_bits(info, "133171")
+    f0 = runtime.take_frames(len(info))
+    return sim.channel_bits(coded, sigma, config.test_snr_index, f0, "i32_trunc" if config.quantize == "trunc_int32" else "f32")
+
+
+def generate_datasets(config: RNNDecoderConfig):
+    """-> (train_info(+-1), train_encoded, test_info(+-1), test_encoded); both sets at the TEST sigma (:206-208)."""
+    sigma = float(config.sigma_vec[config.test_snr_index])
+    out = []
+    for size in (config.training_size, config.test_size):
+        info = generate_input_vectors(config.block_length, size)
+        enc = _transmit(config, info, sigma)
+        pm = info.astype(np.float32)
+        pm[pm == 0] = -1
+        out += [pm, enc]
+    return tuple(out)
+
+
+def build_seq2seq_model(config: RNNDecoderConfig, seed: Optional[int] = None) -> Dict[str, object]:
+    """The reference returns graph tensors; here the dict holds the model parameters (TF LSTMCell
+    layout: kernel [1+H, 4H], gates i,j,f,o, forget_bias 1; linear [H] -> 1) under 'params', and the
+    reference's keys are kept as descriptive placeholders so existing code can index them."""
+    if config.decoder_hidden_units != config.encoder_hidden_units:
+        raise ValueError("decoder initial state = encoder final state needs equal hidden sizes (rnn_viterbi.py:292)")
+    m = _weights.init_lstm(config.encoder_hidden_units, seed)
+    return {"params": m.as_dict(), "encoder_inputs": "encoder_inputs [T, B]", "decoder_inputs": "decoder_inputs [T, B]",
+            "decoder_targets": "decoder_targets [T, B]", "decoder_prediction": "decoder_prediction [T, B]",
+            "loss": "mean squared error", "train_op": "Adam"}
+
+
+def prepare_batch(info_batch: np.ndarray, encoded_batch: np.ndarray, config: RNNDecoderConfig) -> Dict[str, np.ndarray]:
+    """Time-major [T, B, 1] feeds exactly as rnn_viterbi.py:328-377."""
+    info_batch = np.asarray(info_batch)
+    B, L = len(info_batch), config.block_length
+    enc = np.expand_dims(np.transpose(encoded_batch), axis=2)
+    tgt = np.concatenate([info_batch, np.tile(np.concatenate([[config.EOS], np.zeros(L - 1)]), (B, 1))], axis=1)
+    dec = np.concatenate([np.tile([config.EOS], (B, 1)), info_batch, np.zeros((B, L - 1))], axis=1)
+    return {"encoder_inputs": enc, "decoder_inputs": np.expand_dims(np.transpose(dec), axis=2),
+            "decoder_targets": np.expand_dims(np.transpose(tgt), axis=2)}
+
+
+def decode(config: RNNDecoderConfig, params: Dict[str, np.ndarray], encoded: np.ndarray,
+           decoder_inputs: Optional[np.ndarray] = None):
+    """Forward pass on the GPU.  encoded [B, 2L]; decoder_inputs [B, 2L] (teacher forcing) or None
+    (autoregressive).  -> (logits [B, 2L] fp32, hard bits [B, 2L] uint8)."""
+    sim = runtime.get_sim()
+    B, T = np.asarray(encoded).shape
+    h = sim.load_lstm(_weights.LstmModel(**{k: np.asarray(v, np.float32) for k, v in params.items()}))
+    d_y = sim.to_device(np.ascontiguousarray(encoded, dtype=np.float32))
+    d_dec = sim.to_device(np.ascontiguousarray(decoder_inputs, dtype=np.float32)) if decoder_inputs is not None else None
+    logits_b, hard_b = sim.lstm_forward(h, d_y, "f32", d_dec, T, T, B, fast_math=config.fast_math)
+    logits = logits_b.download(np.float32, (B, T))
+    hard = np.unpackbits(hard_b.download(np.uint8, (B, (T + 7) // 8)), axis=1, bitorder="little")[:, :T]
+    for b in (d_y, d_dec, logits_b, hard_b):
+        if b is not None:
+            sim.free(b)
+    sim.lib.nvd_lstm_free(sim.ctx, h)
+    return logits, hard
+
+
+def train_seq2seq(config: RNNDecoderConfig, train_info, train_encoded, test_info, test_encoded,
+                  model: Optional[Dict] = None) -> Tuple[np.ndarray, float]:
+    """Train (MSE, Adam), decode the test set on the GPU, print the reference's lines; -> (predictions [B, L], ber)."""
+    model = model or build_seq2seq_model(config)
+    L = config.block_length
+    batches_per_epoch = int(config.training_size / config.batch_size)
+    max_batches = batches_per_epoch * config.training_epochs
+    print(f"Training for {config.training_epochs} epochs ({max_batches} batches)...")
+    if max_batches > 0:
+        tb = prepare_batch(train_info, train_encoded, config)
+        e, di, dt = (np.transpose(tb[k][:, :, 0]) for k in ("encoder_inputs", "decoder_inputs", "decoder_targets"))
+        model["params"], _ = training.train_lstm(model["params"], e, di, dt, lr=config.learning_rate, batches=max_batches,
+                                                 batch_size=config.batch_size, log_every=batches_per_epoch)
+    print("Training finished!")
+    print("\nEvaluating on test set...")
+    feed = prepare_batch(test_info, test_encoded, config)
+    dec_in = np.transpose(feed["decoder_inputs"][:, :, 0])
+    logits, hard = decode(config, model["params"], np.asarray(test_encoded, dtype=np.float32), dec_in)
+    predictions = hard[:, :L] if config.decision == "sign" else np.zeros((len(hard), L), dtype=np.uint8)
+    info_binary = np.asarray(test_info).copy()
+    info_binary[info_binary == -1] = 0
+    bit_errors = int(np.sum(np.logical_xor(predictions, info_binary)))
+    total_bits = config.test_size * L
+    ber = bit_errors / total_bits
+    print(f"Bit Error Rate: {ber:.6f}")
+    print(f"Bit Errors: {bit_errors}/{total_bits}")
+    return predictions, ber
+
+
+def main() -> None:
+    print("=" * 70)
+    print("RNN-Based Neural Viterbi Decoder (Seq2Seq)")
+    print("=" * 70)
+    config = RNNDecoderConfig()
+    print("\nGenerating datasets...")
+    train_info, train_encoded, test_info, test_encoded = generate_datasets(config)
+    print("\nTraining sequence-to-sequence model...")
+    train_seq2seq(config, train_info, train_encoded, test_info, test_encoded)
+    print("\n" + "=" * 70)
+    print("Decoding complete!")
+    print("=" * 70)
+
+
+if __name__ == "__main__":
+    main()
