@@ -183,6 +183,10 @@ int nvd_mc_set_stage_timing(nvd_ctx* ctx, int enabled);
 /* phase time stamps (clock64) of CTA 0's four groups over their first 64 tiles of a fused run:
  * stamps_host[(tile * 4 + group) * 16 + phase]. */
 int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uint64_t* stamps_host);
+/* same with the A operand in TENSOR MEMORY (written by tcgen05.st, K elements packed two bf16 per
+ * column): a_rows_host = [128][8] uint32. */
+int nvd_debug_umma_probe_ts(nvd_ctx* ctx, int N, int b_lbo_bytes, int b_sbo_bytes, const void* a_rows_host,
+                            const void* b_image_host, float* d_host);
 int nvd_debug_umma_probe(nvd_ctx* ctx, int N, int a_lbo_bytes, int a_sbo_bytes, int b_lbo_bytes,
                          int b_sbo_bytes, const void* a_image_host, const void* b_image_host,
                          float* d_host);

@@ -517,6 +517,51 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, uint32_t a_lb
   if (tid < 32) ptx::tmem_dealloc(tmem_base, 128);
 }
 
+// diagnostics: A operand from TMEM (TS mode).  a_rows: [128][8] packed bf16 pairs (word k2 = elements 2*k2, 2*k2+1)
+__global__ void __launch_bounds__(128, 1) umma_probe_ts_kernel(int N, uint32_t b_lbo, uint32_t b_sbo, const uint32_t* __restrict__ a_rows,
+                                                               const uint4* __restrict__ b_img, float* __restrict__ d, int* abort_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8192 + 8);
+  const uint32_t bar = sbase + 8192;
+  for (int i = tid; i < N * 2; i += 128) reinterpret_cast<uint4*>(smem)[i] = b_img[i];
+  if (tid == 0) { ptx::mbar_init(bar, 1); ptx::mbar_fence_init(); }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+  const uint32_t a_col = 300;   // A operand columns 300..307, D at columns 0..N-1
+  uint32_t w[8];
+  for (int i = 0; i < 8; ++i) w[i] = a_rows[tid * 8 + i];
+  ptx::tmem_st8(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a_col, w);
+  ptx::tmem_wait_st();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::tc_fence_after();
+    ptx::umma_f16_ts(tmem_base, tmem_base + a_col, ptx::make_smem_desc(sbase, b_lbo, b_sbo), ptx::make_idesc_bf16_f32(128, N), 0u);
+    ptx::umma_commit(bar);
+  }
+  if (ptx::mbar_wait_bounded(bar, 0, kMaxWaitMs)) {
+    ptx::tc_fence_after();
+    for (int c = 0; c < N; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+      ptx::tmem_wait_ld();
+      for (int j = 0; j < 32; ++j) d[tid * N + c + j] = __uint_as_float(v[j]);
+    }
+  } else {
+    atomicExch(abort_flag, 10);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 uint16_t f32_to_bf16_host(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -675,6 +720,28 @@ extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uin
     s = nvd_sync(ctx);
   }
   cudaFree(d);
+  return s;
+}
+
+extern "C" int nvd_debug_umma_probe_ts(nvd_ctx* ctx, int N, int b_lbo_bytes, int b_sbo_bytes, const void* a_rows_host,
+                                       const void* b_image_host, float* d_host) {
+  using namespace nvd;
+  NVD_REQUIRE(ctx && a_rows_host && b_image_host && d_host, "null argument");
+  NVD_REQUIRE(N == 32 || N == 64 || N == 128 || N == 256, "N must be 32, 64, 128 or 256");
+  NVD_CUDA(cudaSetDevice(ctx->device));
+  void *da = nullptr, *db = nullptr, *dd = nullptr;
+  NVD_CUDA(cudaMalloc(&da, 4096));
+  NVD_CUDA(cudaMalloc(&db, static_cast<size_t>(N) * 32));
+  NVD_CUDA(cudaMalloc(&dd, static_cast<size_t>(128) * N * 4));
+  NVD_CUDA(cudaMemcpyAsync(da, a_rows_host, 4096, cudaMemcpyHostToDevice, ctx->stream));
+  NVD_CUDA(cudaMemcpyAsync(db, b_image_host, static_cast<size_t>(N) * 32, cudaMemcpyHostToDevice, ctx->stream));
+  NVD_CUDA(cudaMemsetAsync(dd, 0, static_cast<size_t>(128) * N * 4, ctx->stream));
+  umma_probe_ts_kernel<<<1, 128, 8192 + 64, ctx->stream>>>(N, b_lbo_bytes, b_sbo_bytes, static_cast<const uint32_t*>(da),
+                                                           static_cast<const uint4*>(db), static_cast<float*>(dd), ctx->abort_flag);
+  NVD_CHECK_LAUNCH();
+  NVD_CUDA(cudaMemcpyAsync(d_host, dd, static_cast<size_t>(128) * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  const int s = nvd_sync(ctx);
+  cudaFree(da); cudaFree(db); cudaFree(dd);
   return s;
 }
 

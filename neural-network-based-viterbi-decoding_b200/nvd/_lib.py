@@ -75,6 +75,7 @@ _PROTOS = {
     "nvd_mc_stage_ms": ([_vp, C.POINTER(_f)], _i),
     "nvd_mc_set_stage_timing": ([_vp, _i], _i),
     "nvd_debug_tc_timing": ([_vp, _i, _u64, _vp], _i),
+    "nvd_debug_umma_probe_ts": ([_vp, _i, _i, _i, _vp, _vp, _vp], _i),
     "nvd_debug_umma_probe": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
 }
 

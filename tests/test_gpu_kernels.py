@@ -49,6 +49,22 @@ def test_umma_layout_probe(sim, N):
         pytest.fail(f"UMMA layout mismatch: max err {err}; with LBO/SBO swapped {np.abs(d2 - want).max()}")
 
 
+@pytest.mark.parametrize("N", [32, 64])
+def test_umma_ts_mode_probe(sim, N):
+    """A operand from tensor memory (tcgen05.st by the row-owning thread, two bf16 per 32-bit column)."""
+    from nvd import montecarlo as mc, _lib
+    rng = np.random.default_rng(100 + N)
+    A = mc.f32_to_bf16(rng.standard_normal((128, 16)).astype(np.float32))
+    Bm = mc.f32_to_bf16(rng.standard_normal((N, 16)).astype(np.float32))
+    want = mc.bf16_to_f32(A).astype(np.float64) @ mc.bf16_to_f32(Bm).astype(np.float64).T
+    a_rows = (A[:, 0::2].astype(np.uint32) | (A[:, 1::2].astype(np.uint32) << 16)).astype(np.uint32)   # even k in the low half
+    b_img = _canon_image(N, Bm)
+    d = np.zeros((128, N), np.float32)
+    _lib.check(sim.lib.nvd_debug_umma_probe_ts(sim.ctx, N, N * 16, 128, np.ascontiguousarray(a_rows).ctypes.data,
+                                               b_img.ctypes.data, d.ctypes.data))
+    assert np.abs(d - want).max() < 1e-3, np.abs(d - want).max()
+
+
 # ------------------------------------------------------------------------------------------ K0 / K1
 def test_source_small_and_philox(sim):
     B = 1000

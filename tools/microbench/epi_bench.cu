@@ -16,6 +16,17 @@ __device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// LUT tanh: table of bf16 tanh values indexed by the top 16 bits of |x| (clamped); sign re-applied per pair.
+__device__ __forceinline__ uint32_t lut_pair(uint32_t ua, uint32_t ub, uint32_t tab) {
+  uint32_t ia = (ua & 0x7FFF0000u) >> 15, ib = (ub & 0x7FFF0000u) >> 15;
+  ia = min(max(ia, 0x7300u), 0x8100u); ib = min(max(ib, 0x7300u), 0x8100u);
+  uint32_t ra, rb;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ra) : "r"(tab + ia - 0x7300u));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rb) : "r"(tab + ib - 0x7300u));
+  const uint32_t mag = __byte_perm(ra, rb, 0x5410);
+  const uint32_t sgn = __byte_perm(ua, ub, 0x7632) & 0x80008000u;
+  return mag | sgn;
+}
 // VARIANT 0: ld64 + tanh + pack + sts; 1: no LDTM (registers only); 2: no STS; 3: tanh only on regs, no pack
 template <int VARIANT>
 __global__ void __launch_bounds__(512, 1) epi(int iters, float* out) {
@@ -26,6 +37,9 @@ __global__ void __launch_bounds__(512, 1) epi(int iters, float* out) {
   ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
   const uint32_t tm = slot + g * 128 + (uint32_t(r & ~31) << 16);
   const uint32_t a_next = ptx::smem_u32(smem) + g * 32768;
+  const uint32_t tab = ptx::smem_u32(smem) + 4 * 32768;
+  for (int i = tid; i < 2048; i += 512) reinterpret_cast<uint16_t*>(smem + 4 * 32768)[i] = (uint16_t)(0x3F00 + (i & 127));
+  __syncthreads();
   float acc = 0.f;
   uint32_t v0[32], v1[32];
 #pragma unroll
@@ -44,6 +58,8 @@ __global__ void __launch_bounds__(512, 1) epi(int iters, float* out) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
+            constexpr int LUTQ = (VARIANT == 4) ? 4 : (VARIANT == 5) ? 1 : (VARIANT == 6) ? 2 : (VARIANT == 7) ? 3 : 0;  // of 4 words per q: how many via LUT
+            if (VARIANT >= 4 && e < LUTQ) { w[e] = lut_pair(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], tab); continue; }
             float a = ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e]));
             float b = ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e + 1]));
             if (VARIANT == 3) { w[e] = __float_as_uint(a + b); } else w[e] = pack2(a, b);
@@ -63,11 +79,11 @@ __global__ void __launch_bounds__(512, 1) epi(int iters, float* out) {
 template <int V>
 void run(const char* name, int sms) {
   float* d; cudaMalloc(&d, 4);
-  cudaFuncSetAttribute(epi<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768);
+  cudaFuncSetAttribute(epi<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 4096);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  epi<V><<<sms, 512, 4 * 32768>>>(10, d); cudaDeviceSynchronize();
+  epi<V><<<sms, 512, 4 * 32768 + 4096>>>(10, d); cudaDeviceSynchronize();
   const int iters = 2000;
-  cudaEventRecord(e0); epi<V><<<sms, 512, 4 * 32768>>>(iters, d); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  cudaEventRecord(e0); epi<V><<<sms, 512, 4 * 32768 + 4096>>>(iters, d); cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("%-40s %8.3f ms  %6.2f tanh/clk/SM  err=%s\n", name, ms, 512.0 * 128 * iters / (ms * 1e-3) / 1.965e9, cudaGetErrorString(cudaGetLastError()));
 }
@@ -78,5 +94,9 @@ int main() {
   run<1>("tanh + pack + sts.v4 (no LDTM)", p.multiProcessorCount);
   run<2>("ld64 + tanh + pack (no STS)", p.multiProcessorCount);
   run<3>("tanh only (regs)", p.multiProcessorCount);
+  run<4>("ld64 + LUT tanh (all) + sts", p.multiProcessorCount);
+  run<5>("ld64 + 3/4 MUFU + 1/4 LUT + sts", p.multiProcessorCount);
+  run<6>("ld64 + 1/2 MUFU + 1/2 LUT + sts", p.multiProcessorCount);
+  run<7>("ld64 + 1/4 MUFU + 3/4 LUT + sts", p.multiProcessorCount);
   return 0;
 }
