@@ -117,6 +117,11 @@ int nvd_mlp_free(nvd_ctx* ctx, int model);
 int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t B, int precision,
                     float* soft_out, void* hard_out, int hard_bytes);
 int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported);
+/* How the tensor-core path evaluates the hidden-layer tanh (so a numerical model can follow it exactly):
+ * of every 8 consecutive bf16 pairs (16 columns) of a layer, the first *poly_pairs_of_8 use
+ *   tanh(x) ~ sign(x) * u * (c[0] + c[1] u + ... + c[5] u^5),  u = min(|x| * *inv_range, 1)   (fp32, FMA pipe)
+ * and the rest use tanh.approx.f32 (MUFU).  Needs no device. */
+int nvd_tc_tanh_model(int* poly_pairs_of_8, float* coef6, float* inv_range);
 /* host-buffer convenience (synchronous): the `predictions_tensor.eval(feed_dict={x: test_set})`
  * call of src/fnn_viterbi.py:610 — chunked H2D, forward, D2H.  y_host fp32 [B, dims[0]]. */
 int nvd_mlp_decode_host(nvd_ctx* ctx, int model, const float* y_host, int64_t B, int precision,

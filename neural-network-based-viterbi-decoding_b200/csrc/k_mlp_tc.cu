@@ -47,16 +47,18 @@ static_assert(W_BYTES == 39936, "weight image size");
 constexpr int ONES_OFF = W_BYTES;                     // [128 x 16] A chunk, column 0 = 1.0
 constexpr int GROUP_OFF = ONES_OFF + 4096;
 constexpr int A1_OFF = 0;                             // 2 x [128 x 16] (double-buffered by the producer warp)
-constexpr int A2_OFF = 8192;                          // [128 x 128]; A3 / A4 alias into it
-constexpr int A3_OFF = A2_OFF;
-constexpr int A4_OFF = A2_OFF + 16384;
-constexpr int YBUF_OFF = A2_OFF + 32768;              // 128 x 28 B TMA landing buffer
+constexpr int A4_OFF = 8192;                          // [128 x 32] layer-4 A operand (A2 / A3 live in tensor memory)
+constexpr int YBUF_OFF = A4_OFF + 8192;               // 128 x 28 B TMA landing buffer
 constexpr int GROUP_BYTES = YBUF_OFF + 128 * kRowBytes;
 constexpr int BAR_OFF = GROUP_OFF + kGroups * GROUP_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 256;
 constexpr int kThreadsFused = kThreads + 32 * kGroups;  // + one frame-producer warp per group
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(GROUP_BYTES % 128 == 0 && GROUP_OFF % 128 == 0, "alignment");
+
+// tensor-memory columns of one group (128 x 32-bit columns, all 128 lanes):
+//   D1 0..127 -> A2 0..63 (in place) | D2 64..127 -> A3 0..31 | D3 32..63 -> A4 (shared memory) | D4 0..127
+constexpr uint32_t COL_D1 = 0, COL_A2 = 0, COL_D2 = 64, COL_A3 = 0, COL_D3 = 32;
 
 constexpr int A_LBO = 128 * 16;  // bytes between the two K chunks of an A operand (128 rows)
 constexpr int kSBO = 128;        // bytes between 8-row groups
@@ -75,6 +77,7 @@ struct TcParams {
   int hard_bytes;
   int last_act;
   float out_offset;  // constant added to every output accumulator by the last MMA step
+  uint32_t key_mul;  // 32: argmax key = accumulator bits * 32 + (31 - column)
   uint64_t* timing;  // diagnostics: phase time stamps (nullptr = off)
   int use_tma;
   // fused
@@ -100,45 +103,116 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
   return v;
 }
 
-// hidden-layer epilogue over columns [C0, C1): TMEM accumulator (bias already inside) -> tanh ->
-// bf16 -> next layer's A operand (canonical layout: 16-byte K chunk q of row r at q*A_LBO + r*16)
-__device__ __forceinline__ void tanh_pack_store32(const uint32_t (&v)[32], uint32_t a_next, int c, int r) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#ifdef NVD_EXP_NO_TANH
-      w[e] = pack_bf16x2(__uint_as_float(v[8 * q + 2 * e]) * 0.125f, __uint_as_float(v[8 * q + 2 * e + 1]) * 0.125f);
-#else
-      w[e] = pack_bf16x2(ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e])),
-                         ptx::tanh_approx(__uint_as_float(v[8 * q + 2 * e + 1])));
+// ---- tanh on two pipes ---------------------------------------------------------------------------
+// MUFU.TANH runs at 16 results/clk/SM and is the bound of this network (224 tanh per frame), so kPolyOf8 of
+// every 8 bf16 pairs are evaluated on the FMA pipe instead, two elements per packed fp32x2 instruction:
+//   tanh(x) ~ sign(x) * u * Q(u),  u = min(|x| / 3.5, 1)   (FMUL.SAT with |x|: no min/max on the ALU pipe)
+// Q: degree 5, Lawson/minimax fit on [0, 1]; max |error| 1.14e-3 in fp32 arithmetic (tools/fit_tanh_poly.py),
+// below the bf16 rounding step of the stored activation (1.95e-3); |result| <= 0.99931 < 1.
+#ifndef NVD_POLY_OF8
+#define NVD_POLY_OF8 3
 #endif
-    st_shared_v4(a_next + ((c >> 3) + q) * A_LBO + r * 16, w[0], w[1], w[2], w[3]);
+constexpr int kPolyOf8 = NVD_POLY_OF8;
+#define NVD_POLY_C0 3.540826384e+00f
+#define NVD_POLY_C1 -2.634002747e-01f
+#define NVD_POLY_C2 -1.784809705e+01f
+#define NVD_POLY_C3 3.558778774e+01f
+#define NVD_POLY_C4 -2.840123474e+01f
+#define NVD_POLY_C5 8.383429305e+00f
+constexpr float kPolyInvRange = 1.0f / 3.5f;
+
+__device__ __forceinline__ uint64_t dup2(float c) {
+  const uint32_t u = __float_as_uint(c);
+  return (static_cast<uint64_t>(u) << 32) | u;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float sat_abs_scale(uint32_t x) {   // min(|x| * (1/3.5), 1)
+  float u;
+  asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tmul.rn.sat.f32 %0, t, %2;\n\t}" : "=f"(u) : "f"(__uint_as_float(x)), "f"(kPolyInvRange));
+  return u;
+}
+// tanh of two fp32 accumulators -> packed bf16x2 (low half = first element)
+__device__ __forceinline__ uint32_t tanh_pair_poly(uint32_t xa, uint32_t xb) {
+  const float ua = sat_abs_scale(xa), ub = sat_abs_scale(xb);
+  const uint64_t u = (static_cast<uint64_t>(__float_as_uint(ub)) << 32) | __float_as_uint(ua);
+  uint64_t p = fma2(u, dup2(NVD_POLY_C5), dup2(NVD_POLY_C4));
+  p = fma2(p, u, dup2(NVD_POLY_C3));
+  p = fma2(p, u, dup2(NVD_POLY_C2));
+  p = fma2(p, u, dup2(NVD_POLY_C1));
+  p = fma2(p, u, dup2(NVD_POLY_C0));
+  p = mul2(p, u);
+  uint32_t pa = static_cast<uint32_t>(p), pb = static_cast<uint32_t>(p >> 32);
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(pa) : "r"(xa), "r"(pa));   // (x & sign bit) | magnitude
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(pb) : "r"(xb), "r"(pb));
+  return pack_bf16x2(__uint_as_float(pa), __uint_as_float(pb));
+}
+__device__ __forceinline__ uint32_t tanh_pair_mufu(uint32_t xa, uint32_t xb) {
+  return pack_bf16x2(ptx::tanh_approx(__uint_as_float(xa)), ptx::tanh_approx(__uint_as_float(xb)));
+}
+// 32 accumulator columns -> 16 packed bf16 pairs; pair e goes to the FMA pipe when (e mod 8) < kPolyOf8
+__device__ __forceinline__ void tanh_pack32(const uint32_t (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+#ifdef NVD_EXP_NO_TANH
+    w[e] = pack_bf16x2(__uint_as_float(v[2 * e]) * 0.125f, __uint_as_float(v[2 * e + 1]) * 0.125f);
+#else
+    w[e] = ((e & 7) < kPolyOf8) ? tanh_pair_poly(v[2 * e], v[2 * e + 1]) : tanh_pair_mufu(v[2 * e], v[2 * e + 1]);
+#endif
   }
 }
 
-template <int C0, int C1>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint32_t a_next, int r) {
-  if constexpr ((C1 - C0) % 64 == 0) {
-    // two TMEM loads in flight per wait: halves the exposed tcgen05.ld latency
+// hidden-layer epilogue, next layer's A operand in TENSOR MEMORY (TS-mode MMA): accumulator columns
+// [src, src + NCOLS) (bias already inside) -> tanh -> bf16 -> columns [dst, dst + NCOLS/2) of the same lanes,
+// two K elements per 32-bit column.  dst may alias src (dst <= src): every column is read before the
+// store that overwrites it is issued.  Caller: tcgen05.wait::st + fence + group barrier before the MMA.
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_hidden_tmem(uint32_t src, uint32_t dst) {
+  if constexpr (NCOLS % 64 == 0) {
 #pragma unroll
-    for (int c = C0; c < C1; c += 64) {
-      uint32_t v0[32], v1[32];
-      ptx::tmem_ld32(tmem_d + c, v0);
-      ptx::tmem_ld32(tmem_d + c + 32, v1);
+    for (int c = 0; c < NCOLS; c += 64) {
+      uint32_t v0[32], v1[32], w[16];
+      ptx::tmem_ld32(src + c, v0);
+      ptx::tmem_ld32(src + c + 32, v1);
       ptx::tmem_wait_ld();
-      tanh_pack_store32(v0, a_next, c, r);
-      tanh_pack_store32(v1, a_next, c + 32, r);
+      tanh_pack32(v0, w);
+      ptx::tmem_st16(dst + (c >> 1), w);
+      tanh_pack32(v1, w);
+      ptx::tmem_st16(dst + (c >> 1) + 16, w);
     }
   } else {
 #pragma unroll
-    for (int c = C0; c < C1; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_d + c, v);
+    for (int c = 0; c < NCOLS; c += 32) {
+      uint32_t v[32], w[16];
+      ptx::tmem_ld32(src + c, v);
       ptx::tmem_wait_ld();
-      tanh_pack_store32(v, a_next, c, r);
+      tanh_pack32(v, w);
+      ptx::tmem_st16(dst + (c >> 1), w);
     }
+  }
+}
+
+// hidden-layer epilogue, next layer's A operand in SHARED memory (SS-mode MMA, canonical layout: 16-byte
+// K chunk q of row r at q*A_LBO + r*16)
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_hidden_smem(uint32_t src, uint32_t a_next, int r) {
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 32) {
+    uint32_t v[32], w[16];
+    ptx::tmem_ld32(src + c, v);
+    ptx::tmem_wait_ld();
+    tanh_pack32(v, w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(a_next + ((c >> 3) + q) * A_LBO + r * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
   }
 }
 
@@ -164,6 +238,13 @@ __device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_
 // synchronise the group's 128 threads around a hand-off to the tensor core (async proxy)
 __device__ __forceinline__ void group_handoff(int g) {
   ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  ptx::bar_sync(1 + g, 128);
+}
+
+// same for an A operand written to tensor memory with tcgen05.st
+__device__ __forceinline__ void tmem_handoff(int g) {
+  ptx::tmem_wait_st();
   ptx::tc_fence_before();
   ptx::bar_sync(1 + g, 128);
 }
@@ -327,31 +408,22 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     ptx::tc_fence_after();
     if (MODE == MODE_FUSED && issuer_warp && ptx::elect_one()) ptx::mbar_arrive(bar_empty + 8 * buf);   // MMA1 has consumed A1[buf]
 
-    // ---- layer 2: [128 x 128(+16)] x [.. x 64], issued in two halves as A2 becomes available ----
+    // ---- layer 2: [128 x 128(+16)] x [.. x 64]; A2 = tanh(D1) goes back into tensor memory, in place
+    //      over columns 0..63 of D1; D2 lands in columns 64..127 once every thread has read them ----------
     NVD_STAMP(3);
-    epilogue_hidden<0, 64>(tmem_d, grp + A2_OFF, r);
+    epilogue_hidden_tmem<N1>(tmem_d + COL_D1, tmem_d + COL_A2);
     NVD_STAMP(4);
-    group_handoff(g);
+    tmem_handoff(g);
     NVD_STAMP(5);
     if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
+      // bias row first (A = the constant ones chunk in shared memory), then the eight K=16 steps from TMEM
+      ptx::umma_f16_ss(tmem_grp + COL_D2, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
+                       ptx::make_smem_desc(sbase + W2_OFF + (N1 / 16) * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, 0u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)   // D2 overwrites columns 0..63 of D1, which every thread has already read
-        ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A2_OFF + j * 2 * A_LBO, A_LBO, kSBO),
-                         ptx::make_smem_desc(sbase + W2_OFF + j * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, j > 0);
-    }
-    epilogue_hidden<64, 128>(tmem_d, grp + A2_OFF, r);
-    NVD_STAMP(6);
-    group_handoff(g);
-    NVD_STAMP(7);
-    if (issuer_warp && ptx::elect_one()) {
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int j = 4; j < N1 / 16; ++j)
-        ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A2_OFF + j * 2 * A_LBO, A_LBO, kSBO),
+      for (int j = 0; j < N1 / 16; ++j)
+        ptx::umma_f16_ts(tmem_grp + COL_D2, tmem_grp + COL_A2 + 8 * j,
                          ptx::make_smem_desc(sbase + W2_OFF + j * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, 1u);
-      ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
-                       ptx::make_smem_desc(sbase + W2_OFF + (N1 / 16) * 2 * (N2 * 16), N2 * 16, kSBO), idesc64, 1u);
       ptx::umma_commit(bar_mma);
     }
     NVD_STAMP(8);
@@ -359,30 +431,31 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     mma_phase ^= 1;
     ptx::tc_fence_after();
     NVD_STAMP(9);
-    epilogue_hidden<0, N2>(tmem_d, grp + A3_OFF, r);
-    group_handoff(g);
-    NVD_STAMP(10);
 
-    // ---- layer 3: [128 x 64(+16)] x [.. x 32] ----------------------------------------------
+    // ---- layer 3: [128 x 64(+16)] x [.. x 32]; A3 in columns 0..31 (A2 is dead), D3 in columns 32..63 ----
+    epilogue_hidden_tmem<N2>(tmem_d + COL_D2, tmem_d + COL_A3);
+    tmem_handoff(g);
+    NVD_STAMP(10);
     if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
+      ptx::umma_f16_ss(tmem_grp + COL_D3, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
+                       ptx::make_smem_desc(sbase + W3_OFF + (N2 / 16) * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 0u);
 #pragma unroll
       for (int j = 0; j < N2 / 16; ++j)
-        ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A3_OFF + j * 2 * A_LBO, A_LBO, kSBO),
-                         ptx::make_smem_desc(sbase + W3_OFF + j * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, j > 0);
-      ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
-                       ptx::make_smem_desc(sbase + W3_OFF + (N2 / 16) * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 1u);
+        ptx::umma_f16_ts(tmem_grp + COL_D3, tmem_grp + COL_A3 + 8 * j,
+                         ptx::make_smem_desc(sbase + W3_OFF + j * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 1u);
       ptx::umma_commit(bar_mma);
     }
     if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 4); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
     NVD_STAMP(11);
-    epilogue_hidden<0, N3>(tmem_d, grp + A4_OFF, r);
+
+    // ---- layer 4: [128 x 32(+16)] x [.. x 128]; D4 needs all 128 columns of the group, so A4 goes to
+    //      shared memory (N = 128: the SS-mode operand reads take as long as the math) ------------------
+    epilogue_hidden_smem<N3>(tmem_d + COL_D3, grp + A4_OFF, r);
     group_handoff(g);
     NVD_STAMP(12);
-
-    // ---- layer 4: [128 x 32(+16)] x [.. x 128] ---------------------------------------------
     if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
 #pragma unroll
@@ -399,24 +472,25 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
 
     NVD_STAMP(13);
     // ---- output epilogue: argmax, first index on ties.  tanh is monotone, so the decision is taken
-    //      on the pre-activation.  The last MMA step also added the constant out_offset (a power of
-    //      two above sum|w|+|b|, image builder), so every accumulator is POSITIVE and its fp32 bit
-    //      pattern orders like an integer.  Key = bits with the low 5 mantissa bits replaced by
-    //      (31 - j): one integer max tree per 32 columns finds value and index together and prefers
-    //      the smaller index on equal keys; the four column blocks are merged with a strict compare.
-    //      Resolution: 2^-18 * out_offset (2.4e-4 for offset 64) — far inside the bf16 tolerance.
+    //      on the pre-activation.  The last MMA step also added the constant out_offset (a power of two
+    //      >= bound + 2, image builder), so every accumulator lies in [2, 2^17): sign and the four high
+    //      exponent bits are the same for all of them and (bits << 5) still orders like the value.
+    //      Key = bits * 32 + (31 - j): ONE integer multiply-add per column on the FMA pipe (the ALU pipe is
+    //      the busy one here), then an unsigned max tree per 32 columns finds value and index together
+    //      and prefers the smaller index on equal values; the four column blocks are merged with a
+    //      strict compare.  Full fp32 resolution is kept.
     uint32_t best_key = 0u;
     int best_c = 0;
     auto scan32 = [&](const uint32_t (&v)[32], int c) {
-      int k[32];
+      uint32_t k[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) k[j] = static_cast<int>((v[j] & 0xFFFFFFE0u) | static_cast<uint32_t>(31 - j));
+      for (int j = 0; j < 32; ++j) k[j] = v[j] * p.key_mul + static_cast<uint32_t>(31 - j);   // key_mul = 32 (runtime: keeps it an IMAD)
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
 #pragma unroll
         for (int j = 0; j < s; ++j) k[j] = max(k[j], k[j + s]);
-      const uint32_t kb = static_cast<uint32_t>(k[0]);
-      if ((kb & 0xFFFFFFE0u) > (best_key & 0xFFFFFFE0u)) { best_key = kb; best_c = c; }
+      const uint32_t kb = k[0];
+      if ((kb >> 5) > (best_key >> 5)) { best_key = kb; best_c = c; }
       if (MODE == MODE_STAGED && p.soft != nullptr && row < p.B) {
         float4* dst = reinterpret_cast<float4*>(p.soft + row * N4 + c);
 #pragma unroll
@@ -443,6 +517,7 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     const int bi = best_c + 31 - static_cast<int>(best_key & 31u);
     NVD_STAMP(14);
     ptx::tc_fence_before();  // TMEM reads done before the next tile's MMA (issued after a bar_sync)
+    if (MODE == MODE_FUSED) ptx::bar_sync(1 + g, 128);   // staged: the stage-0 hand-off of the next tile does it
     if (MODE == MODE_STAGED) {
       if (p.hard != nullptr && row < p.B) {
         if (p.hard_bytes == 1) static_cast<uint8_t*>(p.hard)[row] = static_cast<uint8_t>(bi);
@@ -632,10 +707,11 @@ int tc_build_image(nvd_ctx* ctx, MlpModel& m, const float* const* W_host, const 
   fill_layer(img.data(), W1_OFF, NIN, N1, W_host[0], b_host[0], 0.0f);
   fill_layer(img.data(), W2_OFF, N1, N2, W_host[1], b_host[1], 0.0f);
   fill_layer(img.data(), W3_OFF, N2, N3, W_host[2], b_host[2], 0.0f);
-  // output layer: |h3| <= 1, so |z| <= bound; add a power of two above it so every accumulator is positive
+  // output layer: |h3| <= 1, so |z| <= bound; add a power of two >= bound + 2 so that every accumulator lies in
+  // [2, 2^17): a common sign / high-exponent prefix, which the argmax key (bits << 5) relies on
   const float bound = fill_layer(img.data(), W4_OFF, N3, N4, W_host[3], b_host[3], 0.0f);
   float offset = 1.0f;
-  while (offset <= bound * 1.0625f && offset < 3.0e38f) offset *= 2.0f;
+  while (offset < bound * 1.0625f + 2.0f && offset < 3.0e38f) offset *= 2.0f;   // accumulators in [2, 2 * offset)
   if (!(offset <= 4096.0f)) {
     set_error("output layer bound %g is too large for the tensor-core argmax (max 4096)", bound);
     return NVD_ERR_UNSUPPORTED;
@@ -662,6 +738,7 @@ int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y
   p.hard_bytes = hard_bytes;
   p.last_act = m.acts[3];
   p.out_offset = m.tc_out_offset;
+  p.key_mul = 32u;
   p.use_tma = (reinterpret_cast<uintptr_t>(y) % 16 == 0) ? 1 : 0;
   p.L = 7;
   if (reinterpret_cast<uintptr_t>(y) % 4 != 0) { set_error("y must be 4-byte aligned"); return NVD_ERR_INVALID; }
@@ -686,10 +763,21 @@ int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float 
   p.L = L;
   p.last_act = m.acts[3];
   p.out_offset = m.tc_out_offset;
+  p.key_mul = 32u;
   return launch_tc<MODE_FUSED>(ctx, p);
 }
 
 }  // namespace nvd
+
+extern "C" int nvd_tc_tanh_model(int* poly_pairs_of_8, float* coef6, float* inv_range) {
+  using namespace nvd;
+  NVD_REQUIRE(poly_pairs_of_8 && coef6 && inv_range, "null argument");
+  *poly_pairs_of_8 = kPolyOf8;
+  const float c[6] = {NVD_POLY_C0, NVD_POLY_C1, NVD_POLY_C2, NVD_POLY_C3, NVD_POLY_C4, NVD_POLY_C5};
+  for (int i = 0; i < 6; ++i) coef6[i] = c[i];
+  *inv_range = kPolyInvRange;
+  return NVD_OK;
+}
 
 extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uint64_t* stamps_host /* [64*4*16] */) {
   using namespace nvd;
@@ -713,6 +801,7 @@ extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uin
   p.L = 7;
   p.last_act = m.acts[3];
   p.out_offset = m.tc_out_offset;
+  p.key_mul = 32u;
   p.timing = d;
   int s = launch_tc<MODE_FUSED>(ctx, p);
   if (s == NVD_OK) {

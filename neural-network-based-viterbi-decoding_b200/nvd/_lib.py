@@ -65,6 +65,7 @@ _PROTOS = {
     "nvd_mlp_free": ([_vp, _i], _i),
     "nvd_mlp_forward": ([_vp, _i, _vp, _i, _i64, _i, _vp, _vp, _i], _i),
     "nvd_mlp_tc_supported": ([_vp, _i, C.POINTER(_i)], _i),
+    "nvd_tc_tanh_model": ([C.POINTER(_i), C.POINTER(_f), C.POINTER(_f)], _i),
     "nvd_mlp_decode_host": ([_vp, _i, _vp, _i64, _i, _vp, _vp], _i),
     "nvd_lstm_load": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)], _i),
     "nvd_lstm_free": ([_vp, _i], _i),
@@ -114,6 +115,14 @@ def load() -> C.CDLL:
 def check(status: int) -> None:
     if status != OK:
         raise NvdError(status, load().nvd_last_error().decode("utf-8", "replace"))
+
+
+def tc_tanh_model():
+    """(poly_pairs_of_8, coef[6], inv_range) of the tensor-core path's two-pipe tanh (include/nvd.h)."""
+    n, r = C.c_int(0), C.c_float(0)
+    coef = (C.c_float * 6)()
+    check(load().nvd_tc_tanh_model(C.byref(n), coef, C.byref(r)))
+    return n.value, [float(c) for c in coef], float(r.value)
 
 
 def device_count() -> int:

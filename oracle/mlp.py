@@ -38,11 +38,30 @@ def forward(x, Ws, bs, acts, dtype=np.float64, return_preact_last=False):
     return (h, z) if return_preact_last else h
 
 
-def forward_bf16_model(x, Ws, bs, acts):
+def tanh_two_pipe(z, tanh_model):
+    """tanh as the tensor-core kernel evaluates it for hidden layers (include/nvd.h,
+    nvd_tc_tanh_model): of every 8 column pairs the first `n` use the fp32 polynomial
+    sign(z) u Q(u), u = min(|z| inv_range, 1); the others exact tanh (tanh.approx)."""
+    n, coef, inv_range = tanh_model
+    z = np.asarray(z, dtype=np.float32)
+    out = np.tanh(z.astype(np.float64)).astype(np.float32)
+    cols = np.arange(z.shape[1])
+    poly_cols = ((cols // 2) % 8) < n
+    u = np.minimum(np.abs(z[:, poly_cols]) * np.float32(inv_range), np.float32(1.0)).astype(np.float32)
+    p = np.full_like(u, np.float32(coef[5]))
+    for c in coef[4::-1]:
+        p = (p.astype(np.float64) * u + np.float32(c)).astype(np.float32)     # one rounding per fma
+    p = (p * u).astype(np.float32)
+    out[:, poly_cols] = np.copysign(p, z[:, poly_cols])
+    return out
+
+
+def forward_bf16_model(x, Ws, bs, acts, tanh_model=None):
     """Numerical model of the tensor-core path: inputs, weights and inter-layer activations
     rounded to bf16, fp32 accumulation, biases bf16 for hidden layers (they are folded
-    into the contraction), exact tanh.  Used to bound the CUDA bf16 kernel tighter than
-    the 2e-2 north-star tolerance."""
+    into the contraction); hidden tanh exact, or the kernel's two-pipe evaluation when
+    `tanh_model` = (poly_pairs_of_8, coef, inv_range) is given.  Used to bound the CUDA bf16
+    kernel tighter than the 2e-2 north-star tolerance."""
     from .channel import bf16_round
     h = bf16_round(np.asarray(x, dtype=np.float32))
     z = None
@@ -50,7 +69,10 @@ def forward_bf16_model(x, Ws, bs, acts):
         Wq = bf16_round(np.asarray(W, dtype=np.float32)).astype(np.float64)
         bq = bf16_round(np.asarray(b, dtype=np.float32)).astype(np.float64)
         z = (h.astype(np.float64) @ Wq + bq).astype(np.float32)
-        h = _act(z, a).astype(np.float32)
+        if tanh_model is not None and a == ACT_TANH and li != len(Ws) - 1:
+            h = tanh_two_pipe(z, tanh_model)
+        else:
+            h = _act(z, a).astype(np.float32)
         if li != len(Ws) - 1:
             h = bf16_round(h)
     return h, z

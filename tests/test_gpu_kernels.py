@@ -205,9 +205,10 @@ def test_mlp_tensor_core_matches_oracle(sim, B):
     pred = hard_b.download(np.int32, (B,))
     yq = mc.bf16_to_f32(y16)
     want64 = omlp.forward(yq, m.Ws, m.bs, m.acts, dtype=np.float64)
-    model16, pre16 = omlp.forward_bf16_model(yq, m.Ws, m.bs, m.acts)
+    from nvd import _lib
+    model16, pre16 = omlp.forward_bf16_model(yq, m.Ws, m.bs, m.acts, tanh_model=_lib.tc_tanh_model())
     assert np.abs(soft - want64).max() <= 2e-2            # north-star bf16 tolerance vs the fp64 oracle
-    assert np.abs(soft - model16).max() <= 1e-2           # vs the bf16 numerical model (tanh.approx only)
+    assert np.abs(soft - model16).max() <= 1e-2           # vs the bf16 numerical model (two-pipe tanh, nvd_tc_tanh_model)
     ok = omlp.top2_margin(want64) >= 5e-2
     assert (pred[ok] == omlp.argmax_first(want64)[ok]).all()
     assert (pred == omlp.argmax_first(soft)).mean() > 0.999   # argmax is taken on the pre-activation

@@ -1,12 +1,15 @@
 #!/bin/bash
 # build experiment variants of libnvd (only k_mlp_tc.cu recompiled): build/var/libnvd_<VARIANT>.so
+# VARIANT = tokens joined by '+': NAME -> -DNVD_EXP_NAME, NAME=VALUE -> -DNVD_NAME=VALUE
 set -e
 cd /root/repo/neural-network-based-viterbi-decoding_b200
 mkdir -p build/var
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 for V in "$@"; do
   DEFS=""
-  for d in $(echo $V | tr '+' ' '); do DEFS="$DEFS -DNVD_EXP_$d"; done
+  for d in $(echo $V | tr '+' ' '); do
+    case "$d" in *=*) DEFS="$DEFS -DNVD_$d";; *) DEFS="$DEFS -DNVD_EXP_$d";; esac
+  done
   nvcc $FLAGS $DEFS -c csrc/k_mlp_tc.cu -o build/var/k_mlp_tc_$V.o &
 done
 wait

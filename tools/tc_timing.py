@@ -6,15 +6,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "neural-network-based-viterbi-decoding_b200"))
 from nvd import montecarlo, weights, _lib
 
-names = ["top", "wait-full", "issue1", "wait1", "epi1a", "sync", "epi1b", "sync", "issue2", "wait2",
+names = ["top", "wait-full", "issue1", "wait1", "epi1", "sync", "issue2", "wait2",
          "epi2+sync", "issue3+wait3", "epi3+sync", "issue4+wait4", "argmax"]
+STAMPS = [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14]
 with montecarlo.Simulator(0) as sim:
     h = sim.load_mlp(weights.load_default_fnn())
     st = np.zeros(64 * 4 * 16, dtype=np.uint64)
     _lib.check(sim.lib.nvd_debug_tc_timing(sim.ctx, h, 1 << 24, st.ctypes.data))
     st = st.reshape(64, 4, 16).astype(np.int64)
     t0 = st[:, :, 0].min()
-    d = np.diff(st[:, :, :15], axis=2)                    # [tile, group, 14] phase durations
+    d = np.diff(st[:, :, STAMPS], axis=2)                    # [tile, group, 14] phase durations
     per_tile = st[1:, :, 0] - st[:-1, :, 0]
     print("tile period per group (clk): median", np.median(per_tile[8:], axis=0), " mean", per_tile[8:].mean())
     med = np.median(d[8:56], axis=(0, 1))
