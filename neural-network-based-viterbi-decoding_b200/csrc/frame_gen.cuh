@@ -31,12 +31,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
+// The same generator with the 20 round keys (key + r * Weyl constant) precomputed on the host and
+// passed as kernel parameters: they arrive as constant-bank operands of the XOR itself, so the
+// per-round key additions disappear from the instruction stream altogether.
+struct PhiloxKeys {
+  uint32_t k[20];   // k[2r] = seed_lo + r * 0x9E3779B9, k[2r+1] = seed_hi + r * 0xBB67AE85
+};
+__host__ inline PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys rk;
+  for (uint32_t r = 0; r < 10; ++r) {
+    rk.k[2 * r] = static_cast<uint32_t>(seed) + r * 0x9E3779B9u;
+    rk.k[2 * r + 1] = static_cast<uint32_t>(seed >> 32) + r * 0xBB67AE85u;
+  }
+  return rk;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c.x;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c.z;
+    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ rk.k[2 * r], static_cast<uint32_t>(p1),
+                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ rk.k[2 * r + 1], static_cast<uint32_t>(p0));
+  }
+  return c;
+}
+
 // counter convention (oracle/philox.py): (frame_lo, frame_hi, block, (snr_idx << 8) | stream)
 __device__ __forceinline__ uint4 frame_words(uint64_t seed, uint64_t frame, uint32_t block,
                                              uint32_t stream_word) {
   return philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32),
                                   block, stream_word),
                        static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+
+__device__ __forceinline__ uint4 frame_words(const PhiloxKeys& rk, uint64_t frame, uint32_t block, uint32_t stream_word) {
+  return philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32), block, stream_word), rk);
 }
 
 __host__ __device__ __forceinline__ uint32_t noise_stream_word(int snr_idx) {
@@ -70,10 +99,16 @@ __device__ __forceinline__ void noise4(uint64_t seed, uint64_t frame, uint32_t b
 // 8 standard normals of symbols 4*block .. 4*block+7: the same arithmetic as two noise4 calls, written
 // stage by stage (both Philox chains, then all lg2, all sqrt, all sin/cos) so that the MUFU
 // operations of the four Box-Muller pairs are in flight together instead of queueing one by one.
+__device__ __forceinline__ void box_muller8(const uint4 x0, const uint4 x1, float z[8]);
 __device__ __forceinline__ void noise8(uint64_t seed, uint64_t frame, uint32_t block,
                                        uint32_t stream_word, float z[8]) {
-  const uint4 x0 = frame_words(seed, frame, block, stream_word);
-  const uint4 x1 = frame_words(seed, frame, block + 1, stream_word);
+  box_muller8(frame_words(seed, frame, block, stream_word), frame_words(seed, frame, block + 1, stream_word), z);
+}
+__device__ __forceinline__ void noise8(const PhiloxKeys& rk, uint64_t frame, uint32_t block,
+                                       uint32_t stream_word, float z[8]) {
+  box_muller8(frame_words(rk, frame, block, stream_word), frame_words(rk, frame, block + 1, stream_word), z);
+}
+__device__ __forceinline__ void box_muller8(const uint4 x0, const uint4 x1, float z[8]) {
   const uint32_t a[4] = {x0.x, x0.z, x1.x, x1.z};
   const uint32_t b[4] = {x0.y, x0.w, x1.y, x1.w};
   float l[4], th[4], r[4];

@@ -81,6 +81,7 @@ struct TcParams {
   uint64_t* timing;  // diagnostics: phase time stamps (nullptr = off)
   int use_tma;
   // fused
+  PhiloxKeys rk;   // Philox round keys of ctx->seed
   uint64_t seed;
   uint64_t frame0;
   uint64_t* counters;
@@ -155,8 +156,20 @@ __device__ __forceinline__ uint32_t tanh_pair_poly(uint32_t xa, uint32_t xb) {
   asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(pb) : "r"(xb), "r"(pb));
   return pack_bf16x2(__uint_as_float(pa), __uint_as_float(pb));
 }
+// MUFU pairs.  NVD_MUFU_PACKED=1 rounds the two accumulators to bf16 first and takes ONE packed
+// tanh.approx.bf16x2 (one issue slot less per pair, same MUFU pipe time); measured SLOWER on B200
+// (2464 vs 2350 clk/tile), so the default stays two fp32 tanh.approx + one pack.
+#ifndef NVD_MUFU_PACKED
+#define NVD_MUFU_PACKED 0
+#endif
 __device__ __forceinline__ uint32_t tanh_pair_mufu(uint32_t xa, uint32_t xb) {
+#if NVD_MUFU_PACKED
+  uint32_t r;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(pack_bf16x2(__uint_as_float(xa), __uint_as_float(xb))));
+  return r;
+#else
   return pack_bf16x2(ptx::tanh_approx(__uint_as_float(xa)), ptx::tanh_approx(__uint_as_float(xb)));
+#endif
 }
 // 32 accumulator columns -> 16 packed bf16 pairs; pair e goes to the FMA pipe when (e mod 8) < kPolyOf8
 __device__ __forceinline__ void tanh_pack32(const uint32_t (&v)[32], uint32_t (&w)[16]) {
@@ -176,26 +189,22 @@ __device__ __forceinline__ void tanh_pack32(const uint32_t (&v)[32], uint32_t (&
 // store that overwrites it is issued.  Caller: tcgen05.wait::st + fence + group barrier before the MMA.
 template <int NCOLS>
 __device__ __forceinline__ void epilogue_hidden_tmem(uint32_t src, uint32_t dst) {
-  if constexpr (NCOLS % 64 == 0) {
+  static_assert(NCOLS % 64 == 0, "two 32-column loads in flight");
+  constexpr int kChunks = NCOLS / 32;
+  // rolling double buffer: chunk i+2 is loaded into the registers of chunk i as soon as those are consumed and
+  // is waited for one chunk later, so only the first tcgen05.ld latency of a layer is exposed
+  // (tcgen05.wait::ld waits for ALL outstanding loads of the thread, hence wait-then-issue).
+  uint32_t v0[32], v1[32], w[16];
+  ptx::tmem_ld32(src, v0);
+  ptx::tmem_ld32(src + 32, v1);
+  ptx::tmem_wait_ld();
 #pragma unroll
-    for (int c = 0; c < NCOLS; c += 64) {
-      uint32_t v0[32], v1[32], w[16];
-      ptx::tmem_ld32(src + c, v0);
-      ptx::tmem_ld32(src + c + 32, v1);
-      ptx::tmem_wait_ld();
-      tanh_pack32(v0, w);
-      ptx::tmem_st16(dst + (c >> 1), w);
-      tanh_pack32(v1, w);
-      ptx::tmem_st16(dst + (c >> 1) + 16, w);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < NCOLS; c += 32) {
-      uint32_t v[32], w[16];
-      ptx::tmem_ld32(src + c, v);
-      ptx::tmem_wait_ld();
-      tanh_pack32(v, w);
-      ptx::tmem_st16(dst + (c >> 1), w);
+  for (int i = 0; i < kChunks; ++i) {
+    if (i & 1) tanh_pack32(v1, w); else tanh_pack32(v0, w);
+    ptx::tmem_st16(dst + 16 * i, w);
+    if (i >= 1 && i + 1 < kChunks) ptx::tmem_wait_ld();        // chunk i+1 (issued one chunk ago) has landed
+    if (i + 2 < kChunks) {
+      if (i & 1) ptx::tmem_ld32(src + 32 * (i + 2), v1); else ptx::tmem_ld32(src + 32 * (i + 2), v0);
     }
   }
 }
@@ -224,7 +233,7 @@ __device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float z[8];
-    noise8(p.seed, f, 2 * half, p.stream_word, z);
+    noise8(p.rk, f, 2 * half, p.stream_word, z);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = 8 * half + 2 * i;
@@ -249,7 +258,7 @@ __device__ __forceinline__ void tmem_handoff(int g) {
   ptx::bar_sync(1 + g, 128);
 }
 
-template <int MODE>
+template <int MODE, bool TIMING>
 __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -355,9 +364,27 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
   int tile_local = 0;
 #define NVD_STAMP(i)                                                                      \
   do {                                                                                    \
-    if (p.timing != nullptr && blockIdx.x == 0 && r == 0 && tile_local < 64)             \
+    if (TIMING && blockIdx.x == 0 && r == 0 && tile_local < 64)                           \
       p.timing[(tile_local * kGroups + g) * 16 + (i)] = static_cast<uint64_t>(clock64()); \
   } while (0)
+
+  // fused mode: layer 1 of tile t+1 is issued from inside the output epilogue of tile t, as soon as the
+  // group's tensor memory has been read out (rotated loop; the first tile is issued here).  The issuer warp
+  // alone waits for the producer's A1 buffer; the others only ever wait for the MMA.
+  auto fused_issue_layer1 = [&](int local) -> bool {
+    const int b = local & 1;
+    if (issuer_warp) {
+      if (!ptx::mbar_wait_bounded(bar_full + 8 * b, (local >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 7); return false; }
+      if (ptx::elect_one()) {
+        ptx::tc_fence_after();
+        ptx::umma_f16_ss(tmem_grp, ptx::make_smem_desc(grp + A1_OFF + b * 4096, A_LBO, kSBO),
+                         ptx::make_smem_desc(sbase + W1_OFF, N1 * 16, kSBO), idesc128, 0u);
+        ptx::umma_commit(bar_mma);
+      }
+    }
+    return true;
+  };
+  if (MODE == MODE_FUSED && !is_producer && tile < num_tiles) fused_issue_layer1(0);
 
   for (; !is_producer && tile < num_tiles; tile += tile_stride, ++tile_local) {
     const int64_t row = tile * 128 + r;
@@ -384,12 +411,11 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
       group_handoff(g);
     } else {
       cls = static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(row)) & lmask;
-      if (!ptx::mbar_wait_bounded(bar_full + 8 * buf, (tile_local >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 7); break; }
     }
     NVD_STAMP(1);
 
-    // ---- layer 1: [128 x 16] x [16 x 128] --------------------------------------------------
-    if (issuer_warp && ptx::elect_one()) {
+    // ---- layer 1: [128 x 16] x [16 x 128] (fused: already in flight) -------------------------
+    if (MODE == MODE_STAGED && issuer_warp && ptx::elect_one()) {
       if (MODE == MODE_STAGED) {
         const int64_t nt = tile + tile_stride;
         if (nt < num_tiles && tile_uses_tma(nt)) {
@@ -432,14 +458,17 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     ptx::tc_fence_after();
     NVD_STAMP(9);
 
-    // ---- layer 3: [128 x 64(+16)] x [.. x 32]; A3 in columns 0..31 (A2 is dead), D3 in columns 32..63 ----
+    // ---- layer 3: [128 x 64(+16)] x [.. x 32]; A3 in columns 0..31 (A2 is dead), D3 in columns 32..63.
+    //      The bias step only needs D3's columns to be free, which they are once layer 2 has completed: it
+    //      is issued before the epilogue and is off the critical path ---------------------------------
+    if (issuer_warp && ptx::elect_one())
+      ptx::umma_f16_ss(tmem_grp + COL_D3, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
+                       ptx::make_smem_desc(sbase + W3_OFF + (N2 / 16) * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 0u);
     epilogue_hidden_tmem<N2>(tmem_d + COL_D2, tmem_d + COL_A3);
     tmem_handoff(g);
     NVD_STAMP(10);
     if (issuer_warp && ptx::elect_one()) {
       ptx::tc_fence_after();
-      ptx::umma_f16_ss(tmem_grp + COL_D3, ptx::make_smem_desc(sbase + ONES_OFF, A_LBO, kSBO),
-                       ptx::make_smem_desc(sbase + W3_OFF + (N2 / 16) * 2 * (N3 * 16), N3 * 16, kSBO), idesc32, 0u);
 #pragma unroll
       for (int j = 0; j < N2 / 16; ++j)
         ptx::umma_f16_ts(tmem_grp + COL_D3, tmem_grp + COL_A3 + 8 * j,
@@ -503,21 +532,40 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
         }
       }
     };
-#ifndef NVD_EXP_NO_ARGMAX
-#pragma unroll
-    for (int c = 0; c < N4; c += 64) {
+    bool pipeline_ok = true;
+    {
+      // rolling loads as in the hidden epilogues.  All of D4 is in registers (or consumed) after the third block's
+      // scan: the group's tensor memory is released there and (fused) layer 1 of the next tile goes out while the
+      // last block is still being scanned.
       uint32_t v0[32], v1[32];
-      ptx::tmem_ld32(tmem_d + c, v0);
-      ptx::tmem_ld32(tmem_d + c + 32, v1);
+      ptx::tmem_ld32(tmem_d, v0);
+      ptx::tmem_ld32(tmem_d + 32, v1);
       ptx::tmem_wait_ld();
-      scan32(v0, c);
-      scan32(v1, c + 32);
-    }
+#ifndef NVD_EXP_NO_ARGMAX
+      scan32(v0, 0);
 #endif
+      ptx::tmem_ld32(tmem_d + 64, v0);
+#ifndef NVD_EXP_NO_ARGMAX
+      scan32(v1, 32);
+#endif
+      ptx::tmem_wait_ld();
+      ptx::tmem_ld32(tmem_d + 96, v1);
+#ifndef NVD_EXP_NO_ARGMAX
+      scan32(v0, 64);
+#endif
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();   // TMEM reads done before the next tile's layer-1 MMA overwrites D4
+      if (MODE == MODE_FUSED) {
+        ptx::bar_sync(1 + g, 128);   // staged: the stage-0 hand-off of the next tile does it
+        if (tile + tile_stride < num_tiles) pipeline_ok = fused_issue_layer1(tile_local + 1);
+      }
+#ifndef NVD_EXP_NO_ARGMAX
+      scan32(v1, 96);
+#endif
+    }
+    if (!pipeline_ok) break;
     const int bi = best_c + 31 - static_cast<int>(best_key & 31u);
     NVD_STAMP(14);
-    ptx::tc_fence_before();  // TMEM reads done before the next tile's MMA (issued after a bar_sync)
-    if (MODE == MODE_FUSED) ptx::bar_sync(1 + g, 128);   // staged: the stage-0 hand-off of the next tile does it
     if (MODE == MODE_STAGED) {
       if (p.hard != nullptr && row < p.B) {
         if (p.hard_bytes == 1) static_cast<uint8_t*>(p.hard)[row] = static_cast<uint8_t>(bi);
@@ -679,9 +727,9 @@ float fill_layer(uint8_t* img, int off, int K, int N, const float* W, const floa
   return bound;
 }
 
-template <int MODE>
+template <int MODE, bool TIMING = false>
 int launch_tc(nvd_ctx* ctx, const TcParams& p) {
-  auto kern = mlp_tc_kernel<MODE>;
+  auto kern = mlp_tc_kernel<MODE, TIMING>;
   NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (p.B + 127) / 128;
   const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, (tiles + kGroups - 1) / kGroups));
@@ -755,6 +803,7 @@ int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float 
   p.abort_flag = ctx->abort_flag;
   p.B = static_cast<int64_t>(frames);
   p.seed = ctx->seed;
+  p.rk = make_philox_keys(ctx->seed);
   p.frame0 = frame0;
   p.counters = counters;
   p.sigma = sigma;
@@ -794,6 +843,7 @@ extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uin
   p.abort_flag = ctx->abort_flag;
   p.B = static_cast<int64_t>(frames);
   p.seed = ctx->seed;
+  p.rk = make_philox_keys(ctx->seed);
   p.counters = d + 64 * 4 * 16;
   p.sigma = 0.5f;
   p.stream_word = noise_stream_word(0);
@@ -803,7 +853,7 @@ extern "C" int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uin
   p.out_offset = m.tc_out_offset;
   p.key_mul = 32u;
   p.timing = d;
-  int s = launch_tc<MODE_FUSED>(ctx, p);
+  int s = launch_tc<MODE_FUSED, true>(ctx, p);
   if (s == NVD_OK) {
     NVD_CUDA(cudaMemcpyAsync(stamps_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     s = nvd_sync(ctx);
