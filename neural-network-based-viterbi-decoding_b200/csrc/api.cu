@@ -131,6 +131,9 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   for (int i = 0; i < 6; ++i)
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  for (cudaEvent_t e : ctx->slice_ev) cudaEventDestroy(e);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NVD_OK;
@@ -560,13 +563,64 @@ int nvd_mc_stage_ms(nvd_ctx* ctx, float* ms5) {
   return NVD_OK;
 }
 
+// Host-buffer step on the fused kernel: the frames are cut into slices; slice i's info words travel host->device
+// on the copy-in stream while the kernel of slice i-1 runs on the context's stream and the decisions of slice
+// i-2 travel back on the copy-out stream (events order the three).  Per frame 1 B crosses PCIe each way.
+static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m, float snr_db, int snr_idx,
+                             const uint8_t* info_host, uint8_t* pred_host, uint64_t* counters_host) {
+  NVD_REQUIRE(cfg->L <= 8, "fused host step: one info byte per frame (L <= 8)");
+  if (!ctx->copy_in) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  if (!ctx->copy_out) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  const uint64_t frames = cfg->frames;
+  // 128 frames per tile, 4 tile streams per SM: slices of a whole number of waves keep the tail small
+  const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * 4 * 128;
+  uint64_t slice = std::max<uint64_t>(wave * 24, 1);
+  const size_t n_slices = static_cast<size_t>((frames + slice - 1) / slice);
+  while (ctx->slice_ev.size() < 2 * n_slices + 1) {
+    cudaEvent_t e;
+    NVD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->slice_ev.push_back(e);
+  }
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  NVD_TRY(ensure_mc_buf(ctx, 2 * al(frames)));
+  uint8_t* d_info = static_cast<uint8_t*>(ctx->mc_buf);
+  uint8_t* d_pred = d_info + al(frames);
+  const float sigma = sigma_of_db(snr_db);
+  NVD_CUDA(cudaMemsetAsync(ctx->counters_scratch, 0, 4 * sizeof(uint64_t), ctx->stream));
+  // the copy streams start after whatever the context's stream was doing (the buffers may be in use)
+  cudaEvent_t ev_start = ctx->slice_ev[2 * n_slices];
+  NVD_CUDA(cudaEventRecord(ev_start, ctx->stream));
+  NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_start, 0));
+  NVD_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_start, 0));
+  size_t s = 0;
+  for (uint64_t off = 0; off < frames; off += slice, ++s) {
+    const uint64_t n = std::min<uint64_t>(slice, frames - off);
+    NVD_CUDA(cudaMemcpyAsync(d_info + off, info_host + off, n, cudaMemcpyHostToDevice, ctx->copy_in));
+    NVD_CUDA(cudaEventRecord(ctx->slice_ev[2 * s], ctx->copy_in));
+    NVD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->slice_ev[2 * s], 0));
+    NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma, snr_idx, cfg->frame0 + off, n, ctx->counters_scratch,
+                                d_info + off, pred_host ? d_pred + off : nullptr));
+    if (pred_host) {
+      NVD_CUDA(cudaEventRecord(ctx->slice_ev[2 * s + 1], ctx->stream));
+      NVD_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->slice_ev[2 * s + 1], 0));
+      NVD_CUDA(cudaMemcpyAsync(pred_host + off, d_pred + off, n, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+  }
+  NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NVD_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
+  NVD_TRY(nvd_sync(ctx));
+  for (int i = 0; i < 4; ++i) counters_host[i] = ctx->counters_pinned[i];
+  return NVD_OK;
+}
+
 int nvd_mc_run_host(nvd_ctx* ctx, const nvd_mc_config* cfg, float snr_db, int snr_idx, const uint8_t* info_host,
                     uint8_t* pred_host, uint64_t* counters_host) {
   CTX_GUARD(ctx);
   MlpModel* m;
   NVD_TRY(validate_mc(ctx, cfg, &m));
   NVD_REQUIRE(info_host && counters_host, "null argument");
-  NVD_REQUIRE(cfg->mode == NVD_MC_STAGED, "the host-buffer step runs the staged pipeline (info words come from the host)");
+  if (cfg->mode == NVD_MC_FUSED) return mc_run_host_fused(ctx, cfg, m, snr_db, snr_idx, info_host, pred_host, counters_host);
   McBuffers b;
   NVD_TRY(carve_mc(ctx, cfg->L, cfg->y_dtype, static_cast<int64_t>(cfg->frames), &b));
   const float sigma = sigma_of_db(snr_db);

@@ -91,6 +91,9 @@ struct nvd_ctx {
   void* pin_buf = nullptr;               // reserved pinned staging
   uint64_t* counters_scratch = nullptr;  // device uint64[4]
   uint64_t* counters_pinned = nullptr;   // pinned uint64[4]
+  // host-buffer fused pipeline: copy-in / copy-out streams and per-slice events (created on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> slice_ev;
   // staged-pipeline stage timing
   cudaEvent_t stage_ev[6] = {nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -120,7 +123,10 @@ int tc_build_image(nvd_ctx* ctx, MlpModel& m, const float* const* W_host, const 
 int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y, int64_t B,
                          float* soft_out, void* hard_out, int hard_bytes);
 // fused: frames [frame0, frame0+frames) generated on chip, counters accumulated
+// info != nullptr: the info words come from that device buffer (one byte per frame) and the decisions go to
+// pred (one byte per frame, may be null) instead of being a function of the frame index
 int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float sigma, int snr_idx,
-                        uint64_t frame0, uint64_t frames, uint64_t* counters);
+                        uint64_t frame0, uint64_t frames, uint64_t* counters, const uint8_t* info = nullptr,
+                        uint8_t* pred = nullptr);
 
 }  // namespace nvd

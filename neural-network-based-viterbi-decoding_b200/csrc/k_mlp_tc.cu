@@ -64,7 +64,10 @@ constexpr int A_LBO = 128 * 16;  // bytes between the two K chunks of an A opera
 constexpr int kSBO = 128;        // bytes between 8-row groups
 constexpr uint32_t kMaxWaitMs = 2000;  // bounded mbarrier waits (wall clock)
 
-enum { MODE_STAGED = 0, MODE_FUSED = 1 };
+enum { MODE_STAGED = 0, MODE_FUSED = 1, MODE_FUSED_IO = 2 };
+// MODE_FUSED_IO = MODE_FUSED with the info words read from a device buffer (one byte per frame, time-packed)
+// and the decisions written back (one byte per frame, MSB-first class index): 2 B of HBM traffic per frame.
+__host__ __device__ constexpr bool mode_is_fused(int mode) { return mode != MODE_STAGED; }
 
 struct TcParams {
   const uint8_t* image;
@@ -81,6 +84,8 @@ struct TcParams {
   uint64_t* timing;  // diagnostics: phase time stamps (nullptr = off)
   int use_tma;
   // fused
+  const uint8_t* info;   // MODE_FUSED_IO: time-packed info word per frame
+  uint8_t* pred;         // MODE_FUSED_IO: decision per frame (may be null)
   PhiloxKeys rk;   // Philox round keys of ctx->seed
   uint64_t seed;
   uint64_t frame0;
@@ -227,9 +232,8 @@ __device__ __forceinline__ void epilogue_hidden_smem(uint32_t src, uint32_t a_ne
 
 // one frame: info word -> encoder -> BPSK + Philox AWGN -> 14 bf16 symbols (+ the 1.0 bias column) as
 // the 8 packed words of its A1 row.  Same device functions as K0/K1/K2 => bit-identical frames.
-__device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_t lmask, uint32_t (&w)[8]) {
-  const uint32_t cls = static_cast<uint32_t>(f) & lmask;
-  const uint32_t coded = encode16(bitrev_L(cls, p.L), 0u, p.code, true, p.L);
+__device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_t info_word, uint32_t (&w)[8]) {
+  const uint32_t coded = encode16(info_word, 0u, p.code, true, p.L);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float z[8];
@@ -259,7 +263,7 @@ __device__ __forceinline__ void tmem_handoff(int g) {
 }
 
 template <int MODE, bool TIMING>
-__global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(mode_is_fused(MODE) ? kThreadsFused : kThreads, 1) mlp_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   const int tid = threadIdx.x;
@@ -267,7 +271,9 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
   // (shared-memory / TMEM addresses, UMMA descriptors) in uniform registers: without it every
   // tcgen05.mma / tcgen05.ld is wrapped in an ELECT + R2UR.BROADCAST "waterfall" loop.
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-  const bool is_producer = (MODE == MODE_FUSED) && warp >= kThreads / 32;   // warps 16..19, one per group
+  constexpr bool kFused = mode_is_fused(MODE);
+  constexpr bool kIO = MODE == MODE_FUSED_IO;
+  const bool is_producer = kFused && warp >= kThreads / 32;   // warps 16..19, one per group
   const int g = is_producer ? (warp - kThreads / 32) : (warp >> 2);
   const int wq = warp & 3;                                                // warp within its group
   const bool issuer_warp = !is_producer && wq == 0;                       // issues this group's MMAs / TMA
@@ -345,8 +351,17 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
 #pragma unroll
         for (int i = 0; i < 8; ++i) { w0[i] = 0x3F003F00u + r0; w1[i] = 0xBF003F00u + r1; }
 #else
-        gen_frame(p, p.frame0 + static_cast<uint64_t>(tile * 128 + r0), lmask, w0);
-        gen_frame(p, p.frame0 + static_cast<uint64_t>(tile * 128 + r1), lmask, w1);
+        const int64_t f0 = tile * 128 + r0, f1 = tile * 128 + r1;
+        uint32_t u0, u1;   // time-packed info words: class-balanced synthetic source, or the caller's
+        if (kIO) {
+          u0 = f0 < p.B ? static_cast<uint32_t>(__ldg(p.info + f0)) & lmask : 0u;
+          u1 = f1 < p.B ? static_cast<uint32_t>(__ldg(p.info + f1)) & lmask : 0u;
+        } else {
+          u0 = bitrev_L(static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(f0)) & lmask, p.L);
+          u1 = bitrev_L(static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(f1)) & lmask, p.L);
+        }
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(f0), u0, w0);
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(f1), u1, w1);
 #endif
         st_shared_v4(a1 + r0 * 16, w0[0], w0[1], w0[2], w0[3]);
         st_shared_v4(a1 + A_LBO + r0 * 16, w0[4], w0[5], w0[6], w0[7]);
@@ -384,13 +399,13 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     }
     return true;
   };
-  if (MODE == MODE_FUSED && !is_producer && tile < num_tiles) fused_issue_layer1(0);
+  if (kFused && !is_producer && tile < num_tiles) fused_issue_layer1(0);
 
   for (; !is_producer && tile < num_tiles; tile += tile_stride, ++tile_local) {
     const int64_t row = tile * 128 + r;
     NVD_STAMP(0);
     uint32_t cls = 0;
-    const int buf = (MODE == MODE_FUSED) ? (tile_local & 1) : 0;
+    const int buf = kFused ? (tile_local & 1) : 0;
     // ---- stage 0: A1 (K padded to 16, column 14 = 1.0).  Staged: this frame's 14 symbols come from
     //      HBM (TMA landing buffer); fused: the producer warp has written the whole tile.
     if (MODE == MODE_STAGED) {
@@ -409,6 +424,8 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
       st_shared_v4(grp + A1_OFF + r * 16, w[0], w[1], w[2], w[3]);
       st_shared_v4(grp + A1_OFF + A_LBO + r * 16, w[4], w[5], w[6], w[7]);
       group_handoff(g);
+    } else if (kIO) {
+      cls = bitrev_L(row < p.B ? static_cast<uint32_t>(__ldg(p.info + row)) & lmask : 0u, p.L);   // label of this frame
     } else {
       cls = static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(row)) & lmask;
     }
@@ -432,7 +449,7 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
     if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 2); break; }
     mma_phase ^= 1;
     ptx::tc_fence_after();
-    if (MODE == MODE_FUSED && issuer_warp && ptx::elect_one()) ptx::mbar_arrive(bar_empty + 8 * buf);   // MMA1 has consumed A1[buf]
+    if (kFused && issuer_warp && ptx::elect_one()) ptx::mbar_arrive(bar_empty + 8 * buf);   // MMA1 has consumed A1[buf]
 
     // ---- layer 2: [128 x 128(+16)] x [.. x 64]; A2 = tanh(D1) goes back into tensor memory, in place
     //      over columns 0..63 of D1; D2 lands in columns 64..127 once every thread has read them ----------
@@ -555,7 +572,7 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
 #endif
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();   // TMEM reads done before the next tile's layer-1 MMA overwrites D4
-      if (MODE == MODE_FUSED) {
+      if (kFused) {
         ptx::bar_sync(1 + g, 128);   // staged: the stage-0 hand-off of the next tile does it
         if (tile + tile_stride < num_tiles) pipeline_ok = fused_issue_layer1(tile_local + 1);
       }
@@ -573,13 +590,14 @@ __global__ void __launch_bounds__(MODE == 1 ? kThreadsFused : kThreads, 1) mlp_t
         else static_cast<int32_t*>(p.hard)[row] = bi;
       }
     } else if (row < p.B) {
+      if (kIO && p.pred != nullptr) p.pred[row] = static_cast<uint8_t>(bi);
       const uint32_t e = (static_cast<uint32_t>(bi) ^ cls) & lmask;
       bit_err += __popc(e);
       frame_err += e ? 1u : 0u;
     }
   }
 
-  if (MODE == MODE_FUSED) {
+  if (kFused) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       bit_err += __shfl_xor_sync(0xFFFFFFFFu, bit_err, o);
@@ -733,7 +751,7 @@ int launch_tc(nvd_ctx* ctx, const TcParams& p) {
   NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (p.B + 127) / 128;
   const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, (tiles + kGroups - 1) / kGroups));
-  kern<<<grid, MODE == MODE_FUSED ? kThreadsFused : kThreads, SMEM_BYTES, ctx->stream>>>(p);
+  kern<<<grid, mode_is_fused(MODE) ? kThreadsFused : kThreads, SMEM_BYTES, ctx->stream>>>(p);
   NVD_CHECK_LAUNCH();
   return NVD_OK;
 }
@@ -795,7 +813,7 @@ int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y
 }
 
 int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float sigma, int snr_idx, uint64_t frame0,
-                        uint64_t frames, uint64_t* counters) {
+                        uint64_t frames, uint64_t* counters, const uint8_t* info, uint8_t* pred) {
   if (frames == 0) return NVD_OK;
   if (2 * L != NIN) { set_error("fused tcgen05 pipeline is compiled for L = %d (got %d)", NIN / 2, L); return NVD_ERR_UNSUPPORTED; }
   TcParams p{};
@@ -813,7 +831,9 @@ int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float 
   p.last_act = m.acts[3];
   p.out_offset = m.tc_out_offset;
   p.key_mul = 32u;
-  return launch_tc<MODE_FUSED>(ctx, p);
+  p.info = info;
+  p.pred = pred;
+  return info ? launch_tc<MODE_FUSED_IO>(ctx, p) : launch_tc<MODE_FUSED>(ctx, p);
 }
 
 }  // namespace nvd

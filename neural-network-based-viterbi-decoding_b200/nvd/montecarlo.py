@@ -315,12 +315,13 @@ class Simulator:
         return out
 
     def run_host(self, h, code, L, snr_db: float, info_host: np.ndarray, pred_host=None, frame0=0, precision="bf16",
-                 y_dtype=None, snr_idx=0) -> np.ndarray:
-        """End-to-end step with HOST buffers: info words in, decisions + counters out (H2D/D2H inside)."""
+                 y_dtype=None, snr_idx=0, mode="staged") -> np.ndarray:
+        """End-to-end step with HOST buffers: info words in, decisions + counters out (H2D/D2H inside).
+        mode "fused": the fused tcgen05 kernel over slices, copies overlapped on two copy streams."""
         if y_dtype is None:
             y_dtype = "bf16" if precision == "bf16" else "f32"
         B = info_host.shape[0]
-        cfg = self._mc_config(h, code, L, precision, "staged", y_dtype, frame0, B)
+        cfg = self._mc_config(h, code, L, precision, mode, y_dtype, frame0, B)
         counters = np.zeros(4, dtype=np.uint64)
         check(self.lib.nvd_mc_run_host(self.ctx, C.byref(cfg), float(snr_db), int(snr_idx), info_host.ctypes.data,
                                        pred_host.ctypes.data if pred_host is not None else None, counters.ctypes.data))

@@ -4,7 +4,7 @@ and size-independent properties at BASELINE.json's full size (2^24 frames / SNR 
 import numpy as np
 import pytest
 
-from oracle import encoders as oenc, mlp as omlp, pipeline as opipe
+from oracle import encoders as oenc, metrics as omet, mlp as omlp, pipeline as opipe
 
 pytestmark = pytest.mark.gpu
 SEED = 20170710
@@ -78,6 +78,24 @@ def test_host_buffer_step_matches_device_step(sim, handle):
     assert (c_host == c_dev).all()
     errs = np.array([bin(int(a) ^ int(b)).count("1") for a, b in zip(pred[:5000], np.arange(5000) & 127)])
     assert errs.sum() <= c_host[0]
+
+
+@pytest.mark.parametrize("frames", [1, 127, 50000, 148 * 4 * 128 * 24 + 4321])
+def test_host_buffer_fused_step_equals_staged_step(sim, handle, frames):
+    """nvd_mc_run_host on the fused kernel (info words from the host, sliced, copies overlapped) returns the same
+    decisions and counters as the staged pipeline for ARBITRARY info words; last size spans two slices."""
+    rng = np.random.default_rng(frames)
+    info = rng.integers(0, 128, frames).astype(np.uint8)             # time-packed words, any order
+    pred_f = np.full(frames, 255, np.uint8)
+    pred_s = np.full(frames, 254, np.uint8)
+    c_f = sim.run_host(handle, "133171", 7, 1.0, info, pred_f, frame0=777, snr_idx=3, mode="fused")
+    c_s = sim.run_host(handle, "133171", 7, 1.0, info, pred_s, frame0=777, snr_idx=3, mode="staged")
+    assert (c_f == c_s).all() and c_f[2] == frames and c_f[3] == 7 * frames
+    assert (pred_f == pred_s).all()
+    be, fe = omet.count_errors(pred_f, oenc.packed_to_class(info, 7), 7)
+    assert [be, fe] == [int(c_f[0]), int(c_f[1])]
+    c_nopred = sim.run_host(handle, "133171", 7, 1.0, info, None, frame0=777, snr_idx=3, mode="fused")
+    assert (c_nopred == c_f).all()
 
 
 def test_full_size_properties(sim, handle):
