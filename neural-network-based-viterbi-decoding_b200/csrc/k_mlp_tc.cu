@@ -183,7 +183,11 @@ __device__ __forceinline__ void tanh_pack32(const uint32_t (&v)[32], uint32_t (&
 #ifdef NVD_EXP_NO_TANH
     w[e] = pack_bf16x2(__uint_as_float(v[2 * e]) * 0.125f, __uint_as_float(v[2 * e + 1]) * 0.125f);
 #else
+#ifdef NVD_EXP_POLY_SPREAD
+    w[e] = ((0x49 >> (e & 7)) & 1) ? tanh_pair_poly(v[2 * e], v[2 * e + 1]) : tanh_pair_mufu(v[2 * e], v[2 * e + 1]);
+#else
     w[e] = ((e & 7) < kPolyOf8) ? tanh_pair_poly(v[2 * e], v[2 * e + 1]) : tanh_pair_mufu(v[2 * e], v[2 * e + 1]);
+#endif
 #endif
   }
 }
@@ -232,8 +236,7 @@ __device__ __forceinline__ void epilogue_hidden_smem(uint32_t src, uint32_t a_ne
 
 // one frame: info word -> encoder -> BPSK + Philox AWGN -> 14 bf16 symbols (+ the 1.0 bias column) as
 // the 8 packed words of its A1 row.  Same device functions as K0/K1/K2 => bit-identical frames.
-__device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_t info_word, uint32_t (&w)[8]) {
-  const uint32_t coded = encode16(info_word, 0u, p.code, true, p.L);
+__device__ __forceinline__ void gen_frame(const TcParams& p, uint64_t f, uint32_t coded, uint32_t (&w)[8]) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float z[8];
@@ -339,6 +342,14 @@ __global__ void __launch_bounds__(mode_is_fused(MODE) ? kThreadsFused : kThreads
   if (is_producer) {
     const int lane = tid & 31;
     int it = 0;
+    // synthetic source: info word = (frame index mod 2^L), and a tile starts at a multiple of 128 >= 2^L frames,
+    // so the code word of "row r of the tile" is the same for every tile: encode the lane's four rows once
+    uint32_t coded_row[4] = {0u, 0u, 0u, 0u};
+    if (!kIO) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        coded_row[q] = encode16(bitrev_L(static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(32 * q + lane)) & lmask, p.L), 0u, p.code, true, p.L);
+    }
     for (; tile < num_tiles; tile += tile_stride, ++it) {
       const int buf = it & 1;
       if (!ptx::mbar_wait_bounded(bar_empty + 8 * buf, ((it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 6); break; }
@@ -352,16 +363,16 @@ __global__ void __launch_bounds__(mode_is_fused(MODE) ? kThreadsFused : kThreads
         for (int i = 0; i < 8; ++i) { w0[i] = 0x3F003F00u + r0; w1[i] = 0xBF003F00u + r1; }
 #else
         const int64_t f0 = tile * 128 + r0, f1 = tile * 128 + r1;
-        uint32_t u0, u1;   // time-packed info words: class-balanced synthetic source, or the caller's
+        uint32_t c0, c1;   // code words: the caller's info words encoded here, or the hoisted synthetic ones
         if (kIO) {
-          u0 = f0 < p.B ? static_cast<uint32_t>(__ldg(p.info + f0)) & lmask : 0u;
-          u1 = f1 < p.B ? static_cast<uint32_t>(__ldg(p.info + f1)) & lmask : 0u;
+          c0 = encode16(f0 < p.B ? static_cast<uint32_t>(__ldg(p.info + f0)) & lmask : 0u, 0u, p.code, true, p.L);
+          c1 = encode16(f1 < p.B ? static_cast<uint32_t>(__ldg(p.info + f1)) & lmask : 0u, 0u, p.code, true, p.L);
         } else {
-          u0 = bitrev_L(static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(f0)) & lmask, p.L);
-          u1 = bitrev_L(static_cast<uint32_t>(p.frame0 + static_cast<uint64_t>(f1)) & lmask, p.L);
+          c0 = q ? coded_row[2] : coded_row[0];
+          c1 = q ? coded_row[3] : coded_row[1];
         }
-        gen_frame(p, p.frame0 + static_cast<uint64_t>(f0), u0, w0);
-        gen_frame(p, p.frame0 + static_cast<uint64_t>(f1), u1, w1);
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(f0), c0, w0);
+        gen_frame(p, p.frame0 + static_cast<uint64_t>(f1), c1, w1);
 #endif
         st_shared_v4(a1 + r0 * 16, w0[0], w0[1], w0[2], w0[3]);
         st_shared_v4(a1 + A_LBO + r0 * 16, w0[4], w0[5], w0[6], w0[7]);
@@ -816,6 +827,7 @@ int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float 
                         uint64_t frames, uint64_t* counters, const uint8_t* info, uint8_t* pred) {
   if (frames == 0) return NVD_OK;
   if (2 * L != NIN) { set_error("fused tcgen05 pipeline is compiled for L = %d (got %d)", NIN / 2, L); return NVD_ERR_UNSUPPORTED; }
+  static_assert(128 % (1 << (NIN / 2)) == 0, "the synthetic source relies on 2^L dividing the tile size");
   TcParams p{};
   p.image = static_cast<const uint8_t*>(m.tc_image);
   p.abort_flag = ctx->abort_flag;
