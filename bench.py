@@ -147,6 +147,11 @@ def run_reference(args, rank, world):
     return 0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_kernel<MODE_FUSED> launch
+# (profiles/r1_ncu_full_fused_summary.txt): the 40 KB weight image and the parameters, nothing per frame
+NCU_DRAM_BYTES_PER_LAUNCH = 83968
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -254,9 +259,12 @@ def main():
     long_region = fused_ms > 1000.0
     peak = peaks["bf16_sustained"] if long_region else peaks["bf16_burst"]
     roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
-                "traffic": None, "kernel": "mlp_tc_kernel<MODE_FUSED>",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "mlp_tc_kernel<MODE_FUSED>",
                 "peak_source": peaks["source"] + (", sustained" if long_region else ", burst"),
-                "note": "co-bound by MUFU: 224 tanh + 28 RNG transcendentals per frame (DESIGN.md)"}
+                "note": "traffic = dram bytes per launch from the committed ncu --set full capture (weights only: the fused "
+                        "kernel generates its frames on chip); not HBM-bound.  Co-limited by MUFU (140 tanh + 28 RNG "
+                        "transcendentals per frame after the FMA-pipe polynomial takes 3/8 of the tanh), the fixed cost of "
+                        "18 small tcgen05.mma per tile and four dependent MMA->epilogue hand-offs per tile (DESIGN.md §4)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
