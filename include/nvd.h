@@ -135,7 +135,8 @@ int nvd_lstm_free(nvd_ctx* ctx, int model);
 /* y [B, T_enc] in y_dtype; dec_in [B, T_dec] fp32 (teacher forcing, src/rnn_viterbi.py:362-371)
  * or NULL = autoregressive (previous hard decision fed back, first input EOS=1).
  * logits_out [B, T_dec] fp32 or NULL; hard_packed [B, ceil(T_dec/8)] (bit t = logit_t > 0) or NULL.
- * fast_math != 0 uses MUFU tanh/sigmoid approximations. */
+ * fast_math: 0 = fp32 with libm-accurate tanh/sigmoid (parity path), 1 = fp32 with MUFU approximations,
+ * 2 = bf16 tensor-core recurrence (tcgen05; weights and h in bf16, fp32 accumulation, c in fp32; H = 16 or 20). */
 int nvd_lstm_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, const float* dec_in,
                      int T_enc, int T_dec, int64_t B, int fast_math, float* logits_out,
                      uint8_t* hard_packed);

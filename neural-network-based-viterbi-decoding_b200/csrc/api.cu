@@ -3,8 +3,11 @@
 // persistent tcgen05 kernel, see k_mlp_tc.cu).  Everything here is host code; there is no CPU
 // compute path — without a CUDA device nvd_ctx_create fails.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <new>
+
+#include <sched.h>
 
 #include "common.cuh"
 
@@ -121,7 +124,7 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
     cudaFree(m.tc_image);
     cudaFree(m.tc_bias_out);
   }
-  for (auto& m : ctx->lstms) cudaFree(m.blob);
+  for (auto& m : ctx->lstms) { cudaFree(m.blob); cudaFree(m.tc_image); }
   cudaFree(ctx->scratch);
   cudaFree(ctx->mc_buf);
   cudaFree(ctx->abort_flag);
@@ -178,12 +181,51 @@ int nvd_free(nvd_ctx* ctx, void* dptr) {
   }
   return NVD_OK;
 }
+// CPUs of the NUMA node the device hangs off (sysfs), empty set if unknown.  Best effort.
+static bool device_numa_cpus(int device, cpu_set_t* set) {
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return false;
+  for (char* c = bus; *c; ++c) *c = static_cast<char>(tolower(*c));
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  int node = -1;
+  const int got = fscanf(f, "%d", &node);
+  fclose(f);
+  if (got != 1 || node < 0) return false;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return false;
+  CPU_ZERO(set);
+  int a = 0, b = 0, n = 0;
+  char sep = 0;
+  // "0-31,64-95" style list
+  while (fscanf(f, "%d", &a) == 1) {
+    b = a;
+    const int c = fgetc(f);
+    if (c == '-') { if (fscanf(f, "%d", &b) != 1) break; sep = static_cast<char>(fgetc(f)); } else sep = static_cast<char>(c);
+    for (int i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET(i, set); ++n; }
+    if (sep != ',') break;
+  }
+  fclose(f);
+  return n > 0;
+}
+
 int nvd_host_alloc(nvd_ctx* ctx, size_t bytes, void** hptr) {
   CTX_GUARD(ctx);
   NVD_REQUIRE(hptr != nullptr, "null hptr");
   *hptr = nullptr;
   if (bytes == 0) return NVD_OK;
-  NVD_CUDA(cudaMallocHost(hptr, bytes));
+  // pinned pages are placed where the allocating thread runs: run on the device's NUMA node for the duration of
+  // the allocation, so that eight ranks' DMA traffic does not all cross the socket interconnect
+  cpu_set_t old_set, node_set;
+  const bool have_old = sched_getaffinity(0, sizeof(old_set), &old_set) == 0;
+  const bool moved = have_old && device_numa_cpus(ctx->device, &node_set) && sched_setaffinity(0, sizeof(node_set), &node_set) == 0;
+  const cudaError_t e = cudaMallocHost(hptr, bytes);
+  if (e == cudaSuccess) memset(*hptr, 0, bytes);
+  if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+  NVD_CUDA(e);
   return NVD_OK;
 }
 int nvd_host_free(nvd_ctx* ctx, void* hptr) {
@@ -417,6 +459,7 @@ int nvd_lstm_load(nvd_ctx* ctx, int H, const float* enc_W, const float* enc_b, c
   m.blob_floats = blob.size();
   NVD_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
   NVD_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (lstm_tc_supported(H)) NVD_TRY(lstm_tc_build_image(m, enc_W, enc_b, dec_W, dec_b, lin_w, lin_b));
   ctx->lstms.push_back(m);
   *model = static_cast<int>(ctx->lstms.size()) - 1;
   return NVD_OK;
@@ -427,7 +470,9 @@ int nvd_lstm_free(nvd_ctx* ctx, int model) {
   NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[model].live, "bad LSTM handle %d", model);
   NVD_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->lstms[model].blob);
+  cudaFree(ctx->lstms[model].tc_image);
   ctx->lstms[model].blob = nullptr;
+  ctx->lstms[model].tc_image = nullptr;
   ctx->lstms[model].live = false;
   return NVD_OK;
 }
@@ -437,6 +482,8 @@ int nvd_lstm_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, const 
   CTX_GUARD(ctx);
   NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[model].live, "bad LSTM handle %d", model);
   NVD_REQUIRE(T_enc >= 1 && T_dec >= 1 && B >= 0 && (B == 0 || y), "bad shape / null input");
+  if (fast_math == 2)   // bf16 tensor-core recurrence (tcgen05, h in tensor memory)
+    return launch_lstm_tc(ctx, ctx->lstms[model], y, y_dtype, dec_in, T_enc, T_dec, B, logits_out, hard_packed);
   return launch_lstm(ctx, ctx->lstms[model], y, y_dtype, dec_in, T_enc, T_dec, B, fast_math, logits_out, hard_packed);
 }
 

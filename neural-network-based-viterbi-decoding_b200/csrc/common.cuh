@@ -67,6 +67,7 @@ struct LstmModel {
   int H = 0;
   float* blob = nullptr;  // [enc Wp | enc b | dec Wp | dec b | lin_w | lin_b], gate-interleaved
   size_t blob_floats = 0;
+  void* tc_image = nullptr;  // bf16 B operands of both cells + linear layer (tensor-core recurrence), H = 16 / 20
 };
 
 }  // namespace nvd
@@ -115,6 +116,13 @@ int launch_count(nvd_ctx* ctx, const void* pred, const void* label, int stride, 
                  int flags, uint64_t* counters);
 int launch_lstm(nvd_ctx* ctx, const LstmModel& m, const void* y, int y_dtype, const float* dec_in,
                 int T_enc, int T_dec, int64_t B, int fast_math, float* logits, uint8_t* hard);
+
+// tensor-core recurrence (k_lstm_tc.cu)
+bool lstm_tc_supported(int H);
+int lstm_tc_build_image(LstmModel& m, const float* enc_W, const float* enc_b, const float* dec_W, const float* dec_b,
+                        const float* lin_w, const float* lin_b);
+int launch_lstm_tc(nvd_ctx* ctx, const LstmModel& m, const void* y, int y_dtype, const float* dec_in,
+                   int T_enc, int T_dec, int64_t B, float* logits, uint8_t* hard);
 
 // tensor-core path (k3_mlp_tc.cu)
 bool tc_shape_supported(const MlpModel& m);

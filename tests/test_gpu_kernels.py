@@ -285,3 +285,42 @@ def test_lstm_matches_oracle(sim, teacher):
     fast_b, _ = sim.lstm_forward(h, sim.to_device(y), "f32", d_dec, 2 * L, 2 * L, B, fast_math=True)
     if teacher:
         assert np.abs(fast_b.download(np.float32, (B, 2 * L)) - want).max() <= 2e-2   # MUFU tanh path
+
+
+@pytest.mark.parametrize("H,B", [(20, 300), (16, 129), (20, 148 * 4 * 128 + 77)])
+def test_lstm_tensor_core_recurrence(sim, H, B):
+    """fast_math = 2: the tcgen05 recurrence (bf16 weights and h, fp32 accumulation and cell state) against the
+    fp64 oracle, teacher-forced over 200 + 200 steps: bf16 tolerance, decisions equal away from zero; the packed
+    hard decisions are the signs of its own logits; autoregressive mode agrees with the fp32 kernel's decisions."""
+    from nvd import weights
+    L = 100
+    p = olstm.init_params(H, seed=4)
+    rng = np.random.default_rng(9)
+    p["enc_b"] = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    p["dec_b"] = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    p["lin_b"] = np.array([0.05], np.float32)
+    info = rng.integers(0, 2, (B, L))
+    y = (2.0 * oenc.encode_133171(info) - 1.0 + 0.6 * rng.standard_normal((B, 2 * L))).astype(np.float32)
+    _, dec_in, _ = olstm.prepare_batch(2.0 * info - 1.0, y, L)
+    h = sim.load_lstm(weights.LstmModel(**p))
+    d_y, d_dec = sim.to_device(y), sim.to_device(dec_in.astype(np.float32))
+    logits_b, hard_b = sim.lstm_forward(h, d_y, "f32", d_dec, 2 * L, 2 * L, B, fast_math=2)
+    got = logits_b.download(np.float32, (B, 2 * L))
+    hard = np.unpackbits(hard_b.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
+    assert (hard == (got > 0)).all()
+    n_chk = min(B, 2000)
+    want = olstm.seq2seq_forward(y[:n_chk], dec_in[:n_chk], p, dtype=np.float64)
+    err = np.abs(got[:n_chk] - want)
+    assert err.max() <= 3e-2, err.max()                   # bf16 operands through 400 recurrent steps
+    ok = np.abs(want) >= 5e-2
+    assert (hard[:n_chk][ok] == (want > 0)[ok]).all()
+    # the tail of the batch (last, partial tile) against the fp32 kernel
+    ref_b, _ = sim.lstm_forward(h, d_y, "f32", d_dec, 2 * L, 2 * L, B, fast_math=False, want_hard=False)
+    ref = ref_b.download(np.float32, (B, 2 * L))
+    assert np.abs(got[-200:] - ref[-200:]).max() <= 3e-2
+    # autoregressive: decisions fed back
+    _, hard_a = sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=2, want_logits=False)
+    _, hard_r = sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=False, want_logits=False)
+    ha = np.unpackbits(hard_a.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
+    hr = np.unpackbits(hard_r.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
+    assert (ha == hr).all(axis=1).mean() > 0.9            # a flipped near-zero logit changes the fed-back path

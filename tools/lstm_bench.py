@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""K4 throughput: persistent LSTM seq2seq decoder, (133,171) L = 100 blocks (BASELINE.json configs[3])."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "neural-network-based-viterbi-decoding_b200"))
+from nvd import montecarlo, weights
+from oracle import lstm as olstm
+
+L, H = 100, 20
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 8
+p = olstm.init_params(H, seed=4)
+with montecarlo.Simulator(0) as sim:
+    h = sim.load_lstm(weights.LstmModel(**p))
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((B, 2 * L)).astype(np.float32)
+    d_y = sim.to_device(y)
+    for fast in (0, 1, 2):
+        for _ in range(2):
+            sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=fast, want_logits=False)
+        sim.sync()
+        e0, e1 = sim.event(), sim.event()
+        sim.record(e0)
+        reps = 3
+        for _ in range(reps):
+            sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=fast, want_logits=False)
+        sim.record(e1); sim.sync()
+        ms = sim.elapsed_ms(e0, e1) / reps
+        fma = B * 400 * (1 + H) * H * 4
+        print(f"fast_math={fast}: B={B} {ms:.3f} ms  {B / ms / 1e3:.2f} Mframes/s  {B * L / ms / 1e6:.3f} Gbit/s  "
+              f"{fma / ms / 1e9:.2f} TFMA/s ({fma / ms / 1e9 / (148 * 128 * 1.965e-3):.1%} of the FP32 FMA peak)")
