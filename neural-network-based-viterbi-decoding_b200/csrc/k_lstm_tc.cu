@@ -28,6 +28,8 @@ constexpr int kGroups = 4;
 constexpr int kThreads = 128 * kGroups;
 constexpr int KP = 32;                 // padded contraction length: x, h[0..H), 1.0, zeros
 constexpr uint32_t kMaxWaitMs = 2000;
+constexpr int kWin = 32;                                  // time steps per staged input / logit window
+constexpr int kTileBytes = 128 * (kWin + 1) * 4;          // [128 frames][32 steps] fp32, padded rows
 constexpr uint32_t COL_D = 0, COL_A = 96;   // tensor-memory columns of a group: gates 0..4H-1, A operand 96..111
 
 struct LstmTcParams {
@@ -54,6 +56,42 @@ __device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t i
   return static_cast<float>(__ldg(static_cast<const int32_t*>(p) + i));
 }
 
+// tanh of two accumulators on the FMA pipe (packed fp32x2), same polynomial as the feed-forward decoder
+// (k_mlp_tc.cu, tools/fit_tanh_poly.py): tanh(x) ~ sign(x) u Q(u), u = min(|x| / 3.5, 1), max |error| 1.14e-3
+// Of the 8 gate pairs of every 4 units ((i, j) and (f, o) per unit) this many are evaluated by the polynomial,
+// (i, j) pairs first; tanh(c') always goes to the MUFU.  Measured on B200 (tools/lstm_bench.py, H = 20, T = 200 + 200):
+// 0: 89 Mframes/s, 4: 112 Mframes/s, see DESIGN.md for the rest of the sweep.
+#ifndef NVD_LSTM_POLY_PAIRS
+#define NVD_LSTM_POLY_PAIRS 4
+#endif
+__device__ __forceinline__ uint64_t dup2(float c) {
+  const uint32_t u = __float_as_uint(c);
+  return (static_cast<uint64_t>(u) << 32) | u;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void tanh_pair_poly(uint32_t xa, uint32_t xb, float& ta, float& tb) {
+  float ua, ub;
+  asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tmul.rn.sat.f32 %0, t, 0f3E924925;\n\t}" : "=f"(ua) : "f"(__uint_as_float(xa)));
+  asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tmul.rn.sat.f32 %0, t, 0f3E924925;\n\t}" : "=f"(ub) : "f"(__uint_as_float(xb)));
+  const uint64_t u = (static_cast<uint64_t>(__float_as_uint(ub)) << 32) | __float_as_uint(ua);
+  uint64_t q = fma2(u, dup2(8.383429305e+00f), dup2(-2.840123474e+01f));
+  q = fma2(q, u, dup2(3.558778774e+01f));
+  q = fma2(q, u, dup2(-1.784809705e+01f));
+  q = fma2(q, u, dup2(-2.634002747e-01f));
+  q = fma2(q, u, dup2(3.540826384e+00f));
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(q), "l"(u));
+  uint32_t pa = static_cast<uint32_t>(r), pb = static_cast<uint32_t>(r >> 32);
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(pa) : "r"(xa), "r"(pa));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(pb) : "r"(xb), "r"(pb));
+  ta = __uint_as_float(pa);
+  tb = __uint_as_float(pb);
+}
+
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams p) {
   constexpr int N = 4 * H;
@@ -66,7 +104,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
   const bool issuer_warp = wq == 0;
   const int r = tid & 127;
   constexpr int LIN_OFF = 2 * kCellBytes;
-  constexpr int BAR_OFF = LIN_OFF + ((H + 1 + 3) & ~3) * 4;
+  constexpr int TILE_OFF = LIN_OFF + ((H + 1 + 3) & ~3) * 4;          // per group: input window + logit window
+  constexpr int BAR_OFF = TILE_OFF + kGroups * 2 * kTileBytes;
+  float (*xs)[kWin + 1] = reinterpret_cast<float (*)[kWin + 1]>(smem + TILE_OFF + g * 2 * kTileBytes);
+  float (*ls)[kWin + 1] = reinterpret_cast<float (*)[kWin + 1]>(smem + TILE_OFF + g * 2 * kTileBytes + kTileBytes);
   const uint32_t bar_mma = sbase + BAR_OFF + 8 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 64);
   const float* s_lin = reinterpret_cast<const float*>(smem + LIN_OFF);
@@ -94,29 +135,47 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
        tile += static_cast<int64_t>(gridDim.x) * kGroups) {
     const int64_t f = tile * 128 + r;
     const bool live = f < p.B;
-    float c[H], h[H];
+    float c[H];
 #pragma unroll
-    for (int u = 0; u < H; ++u) { c[u] = 0.0f; h[u] = 0.0f; }
-    float prev = 1.0f;   // EOS (rnn_viterbi.py:93)
+    for (int u = 0; u < H; ++u) c[u] = 0.0f;
     uint32_t bits = 0;
-    float x = live ? load_as_f32(p.y, p.y_dtype, f * p.T_enc) : 0.0f;
     const int T = p.T_enc + p.T_dec;
+    // A operand of a step: (x, h0) (h1, h2) ... (h[H-1], 1.0) 0 ... as bf16 pairs, two per 32-bit column
+    uint32_t w[H / 2 + 1];
+    // inputs travel through a [128 x 32] shared window filled with coalesced row reads (one frame's 32 consecutive
+    // time steps per warp request); per-thread strided reads made the run time depend on where the buffer landed
+    auto load_window = [&](int t0) {
+#pragma unroll 4
+      for (int idx = r; idx < 128 * kWin; idx += 128) {
+        const int rr = idx >> 5, sidx = idx & 31, tt = t0 + sidx;
+        const int64_t ff = tile * 128 + rr;
+        float v = 0.0f;
+        if (ff < p.B) {
+          if (tt < p.T_enc) v = load_as_f32(p.y, p.y_dtype, ff * p.T_enc + tt);
+          else if (p.dec_in != nullptr && tt < T) v = __ldg(p.dec_in + ff * p.T_dec + (tt - p.T_enc));
+        }
+        xs[rr][sidx] = v;
+      }
+    };
+    ptx::bar_sync(1 + g, 128);   // the previous tile's readers are done with the windows
+    load_window(0);
+    ptx::bar_sync(1 + g, 128);
+    w[0] = pack_bf16x2(xs[r][0], 0.0f);
+#pragma unroll
+    for (int i = 1; i < H / 2; ++i) w[i] = 0u;
+    w[H / 2] = pack_bf16x2(0.0f, 1.0f);
     for (int t = 0; t < T; ++t) {
       const bool dec = t >= p.T_enc;
       const int td = t - p.T_enc;
-      // ---- A operand of this step: (x, h0) (h1, h2) ... (h[H-1], 1.0) 0 ... as bf16 pairs, two per column
+      // ---- hand the A operand over and start the step's two K = 16 MMAs -------------------------
       {
-        uint32_t w[16];
-        w[0] = pack_bf16x2(x, h[0]);
+        uint32_t wa[16];
 #pragma unroll
-        for (int i = 1; i < H / 2; ++i) w[i] = pack_bf16x2(h[2 * i - 1], h[2 * i]);
-        w[H / 2] = pack_bf16x2(h[H - 1], 1.0f);
-#pragma unroll
-        for (int i = H / 2 + 1; i < 16; ++i) w[i] = 0u;
-        ptx::tmem_st16(tmem_d + COL_A, w);
+        for (int i = 0; i < 16; ++i) wa[i] = (i <= H / 2) ? w[i] : 0u;
+        ptx::tmem_st16(tmem_d + COL_A, wa);
       }
       ptx::tmem_wait_st();
-      ptx::tc_fence_before();
+      ptx::tc_fence_before();   // also orders the previous step's gate reads before this step's MMA
       ptx::bar_sync(1 + g, 128);
       if (issuer_warp && ptx::elect_one()) {
         ptx::tc_fence_after();
@@ -127,39 +186,64 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
                            ptx::make_smem_desc(wbase + j * 2 * (N * 16), N * 16, 128), idesc, j > 0);
         ptx::umma_commit(bar_mma);
       }
-      // next step's input while the MMA runs
-      float x_next = 0.0f;
-      if (t + 1 < p.T_enc) x_next = live ? load_as_f32(p.y, p.y_dtype, f * p.T_enc + t + 1) : 0.0f;
-      else if (t + 1 < T && p.dec_in != nullptr) x_next = live ? __ldg(p.dec_in + f * p.T_dec + (t + 1 - p.T_enc)) : 0.0f;
-      if (!ptx::mbar_wait_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 20); ok = false; break; }
+      // next window of inputs while the MMA runs (every 32 steps; the hand-off barrier above separates it from
+      // the last reads of the previous window)
+      if (((t + 1) & (kWin - 1)) == 0 && t + 1 < T) { load_window(t + 1); ptx::bar_sync(1 + g, 128); }
+      float x_next = xs[r][(t + 1) & (kWin - 1)];
+      if (t + 1 == p.T_enc && p.dec_in == nullptr) x_next = 1.0f;   // EOS opens the autoregressive decoder (rnn_viterbi.py:93)
+      if (!ptx::mbar_spin_bounded(bar_mma, mma_phase, kMaxWaitMs)) { atomicExch(p.abort_flag, 20); ok = false; break; }
       mma_phase ^= 1;
       ptx::tc_fence_after();
-      // ---- gates: 16 columns = 4 units x (i/2, j, (f+1)/2, o/2) ---------------------------------
+      // ---- gates: 16 columns = 4 units x (i/2, j, (f+1)/2, o/2); rolling double buffer of tcgen05.ld ----
+      float lg = s_lin[H], h_carry = 0.0f, h0 = 0.0f;
+      uint32_t v0[16], v1[16];
+      ptx::tmem_ld16(tmem_d + COL_D, v0);
+      ptx::tmem_ld16(tmem_d + COL_D + 16, v1);
+      ptx::tmem_wait_ld();
 #pragma unroll
       for (int q = 0; q < H / 4; ++q) {
-        uint32_t v[16];
-        ptx::tmem_ld16(tmem_d + COL_D + 16 * q, v);
-        ptx::tmem_wait_ld();
+        float hq[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int u = 4 * q + i;
-          const float si = fmaf(ptx::tanh_approx(__uint_as_float(v[4 * i])), 0.5f, 0.5f);
-          const float tj = ptx::tanh_approx(__uint_as_float(v[4 * i + 1]));
-          const float sf = fmaf(ptx::tanh_approx(__uint_as_float(v[4 * i + 2])), 0.5f, 0.5f);
-          const float so = fmaf(ptx::tanh_approx(__uint_as_float(v[4 * i + 3])), 0.5f, 0.5f);
+          const uint32_t* v = (q & 1) ? v1 : v0;
+          float ti, tj, tf, to;
+          if (i < NVD_LSTM_POLY_PAIRS) tanh_pair_poly(v[4 * i], v[4 * i + 1], ti, tj);
+          else { ti = ptx::tanh_approx(__uint_as_float(v[4 * i])); tj = ptx::tanh_approx(__uint_as_float(v[4 * i + 1])); }
+          if (i + 4 < NVD_LSTM_POLY_PAIRS) tanh_pair_poly(v[4 * i + 2], v[4 * i + 3], tf, to);
+          else { tf = ptx::tanh_approx(__uint_as_float(v[4 * i + 2])); to = ptx::tanh_approx(__uint_as_float(v[4 * i + 3])); }
+          const float si = fmaf(ti, 0.5f, 0.5f);
+          const float sf = fmaf(tf, 0.5f, 0.5f);
+          const float so = fmaf(to, 0.5f, 0.5f);
           c[u] = fmaf(sf, c[u], si * tj);
-          h[u] = so * ptx::tanh_approx(c[u]);
+          hq[i] = so * ptx::tanh_approx(c[u]);
+          lg = fmaf(hq[i], s_lin[u], lg);   // every step: no branch on the phase inside the unrolled gate code
         }
+        if (q >= 1 && q + 1 < H / 4) ptx::tmem_wait_ld();          // chunk q+1 (issued one chunk ago) has landed
+        if (q + 2 < H / 4) { if (q & 1) ptx::tmem_ld16(tmem_d + COL_D + 16 * (q + 2), v1); else ptx::tmem_ld16(tmem_d + COL_D + 16 * (q + 2), v0); }
+        // pack: words (h[4q-1], h[4q]) (h[4q+1], h[4q+2]); h[4q+3] is carried into the next chunk
+        if (q == 0) h0 = hq[0]; else w[2 * q] = pack_bf16x2(h_carry, hq[0]);
+        w[2 * q + 1] = pack_bf16x2(hq[1], hq[2]);
+        h_carry = hq[3];
       }
-      ptx::tc_fence_before();   // gate reads done before the next step's MMA overwrites them (after the barrier)
+      w[H / 2] = pack_bf16x2(h_carry, 1.0f);
+      float x = x_next;
       if (dec) {
-        float lg = s_lin[H];
-#pragma unroll
-        for (int u = 0; u < H; ++u) lg = fmaf(h[u], s_lin[u], lg);
         const bool one = lg > 0.0f;
         bits |= (one ? 1u : 0u) << (td & 31);
-        prev = one ? 1.0f : -1.0f;
-        if (p.logits != nullptr && live) p.logits[f * p.T_dec + td] = lg;
+        if (p.dec_in == nullptr) x = one ? 1.0f : -1.0f;   // autoregressive: the decision is the next input
+        if (p.logits != nullptr) {
+          ls[r][td & (kWin - 1)] = lg;
+          if ((td & (kWin - 1)) == kWin - 1 || td == p.T_dec - 1) {   // flush the window with coalesced row writes
+            const int td0 = td & ~(kWin - 1);
+            ptx::bar_sync(1 + g, 128);
+            for (int idx = r; idx < 128 * kWin; idx += 128) {
+              const int rr = idx >> 5, sidx = idx & 31;
+              const int64_t ff = tile * 128 + rr;
+              if (ff < p.B && td0 + sidx <= td) p.logits[ff * p.T_dec + td0 + sidx] = ls[rr][sidx];
+            }
+          }
+        }
         if (p.hard != nullptr && live && ((td & 31) == 31 || td == p.T_dec - 1)) {
           const int byte0 = (td >> 5) << 2;
 #pragma unroll
@@ -168,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
           bits = 0;
         }
       }
-      x = (t + 1 >= p.T_enc && p.dec_in == nullptr) ? prev : x_next;
+      w[0] = pack_bf16x2(x, h0);
     }
   }
   ptx::tc_fence_before();
@@ -203,7 +287,7 @@ void fill_cell(uint8_t* img, int H, const float* W /* [1+H, 4H] */, const float*
 template <int H>
 int launch_h(nvd_ctx* ctx, const LstmTcParams& p) {
   constexpr int N = 4 * H;
-  const int smem = 2 * N * KP * 2 + ((H + 1 + 3) & ~3) * 4 + 128;
+  const int smem = 2 * N * KP * 2 + ((H + 1 + 3) & ~3) * 4 + kGroups * 2 * kTileBytes + 128;
   auto kern = lstm_tc_kernel<H>;
   NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (p.B + 127) / 128;

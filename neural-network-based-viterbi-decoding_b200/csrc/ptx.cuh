@@ -36,6 +36,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// non-blocking probe (mbarrier.test_wait never suspends the thread; try_wait may, for a system-dependent time)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -46,11 +58,28 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // the global timer, not on the number of probes.
 __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t max_ms) {
   if (mbar_try_wait(bar, parity)) return true;
-  const uint64_t t0 = global_timer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > static_cast<uint64_t>(max_ms) * 1000000ull) return false;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spin & 1023u) == 0u) {   // the global timer is slow to read: look at it once per 1024 probes
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > static_cast<uint64_t>(max_ms) * 1000000ull) return false;
+    }
   }
-  return true;
+}
+
+// Same bound, pure polling: for waits that are known to be short (a two-instruction MMA chain) and frequent.
+__device__ __forceinline__ bool mbar_spin_bounded(uint32_t bar, uint32_t parity, uint32_t max_ms) {
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_test_wait(bar, parity)) return true;
+    if ((spin & 4095u) == 0u) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > static_cast<uint64_t>(max_ms) * 1000000ull) return false;
+    }
+  }
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------

@@ -15,15 +15,19 @@ with montecarlo.Simulator(0) as sim:
     rng = np.random.default_rng(0)
     y = rng.standard_normal((B, 2 * L)).astype(np.float32)
     d_y = sim.to_device(y)
+    from nvd import _lib
+    d_hard = sim.alloc(B * 25)            # buffers allocated once: no cudaMalloc inside the timed region
+    def step(fast):
+        _lib.check(sim.lib.nvd_lstm_forward(sim.ctx, h, d_y.ptr, _lib.DTYPES["f32"], None, 2 * L, 2 * L, B, fast, None, d_hard.ptr))
     for fast in (0, 1, 2):
         for _ in range(2):
-            sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=fast, want_logits=False)
+            step(fast)
         sim.sync()
         e0, e1 = sim.event(), sim.event()
         sim.record(e0)
-        reps = 3
+        reps = 5
         for _ in range(reps):
-            sim.lstm_forward(h, d_y, "f32", None, 2 * L, 2 * L, B, fast_math=fast, want_logits=False)
+            step(fast)
         sim.record(e1); sim.sync()
         ms = sim.elapsed_ms(e0, e1) / reps
         fma = B * 400 * (1 + H) * H * 4
