@@ -115,7 +115,12 @@ def decode(config: RNNDecoderConfig, params: Dict[str, np.ndarray], encoded: np.
     h = sim.load_lstm(_weights.LstmModel(**{k: np.asarray(v, np.float32) for k, v in params.items()}))
     d_y = sim.to_device(np.ascontiguousarray(encoded, dtype=np.float32))
     d_dec = sim.to_device(np.ascontiguousarray(decoder_inputs, dtype=np.float32)) if decoder_inputs is not None else None
-    logits_b, hard_b = sim.lstm_forward(h, d_y, "f32", d_dec, T, T, B, fast_math=config.fast_math)
+    # fast_math: False / 0 = fp32 parity path, True / 1 = fp32 with MUFU approximations, 2 = bf16 tcgen05 recurrence;
+    # runtime.set_precision("bf16") selects the tensor-core recurrence where the hidden size is covered (16, 20)
+    fast = int(config.fast_math)
+    if runtime.precision() == "bf16" and config.encoder_hidden_units in (16, 20):
+        fast = 2
+    logits_b, hard_b = sim.lstm_forward(h, d_y, "f32", d_dec, T, T, B, fast_math=fast)
     logits = logits_b.download(np.float32, (B, T))
     hard = np.unpackbits(hard_b.download(np.uint8, (B, (T + 7) // 8)), axis=1, bitorder="little")[:, :T]
     for b in (d_y, d_dec, logits_b, hard_b):

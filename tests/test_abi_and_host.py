@@ -40,7 +40,7 @@ def test_library_contains_blackwell_tensor_core_code(built):
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "MUFU.TANH"):
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "MUFU.TANH", "FFMA2"):
         assert mnemonic in r.stdout, mnemonic
     assert "HMMA.16" not in r.stdout            # no legacy mma.sync path
 
