@@ -24,13 +24,17 @@ namespace nvd {
 
 namespace {
 
-constexpr int kGroups = 4;
+#ifndef NVD_LSTM_GROUPS
+#define NVD_LSTM_GROUPS 5
+#endif
+constexpr int kGroups = NVD_LSTM_GROUPS;
+constexpr int kGroupCols = kGroups == 4 ? 128 : 96;       // tensor-memory columns per group
 constexpr int kThreads = 128 * kGroups;
 constexpr int KP = 32;                 // padded contraction length: x, h[0..H), 1.0, zeros
 constexpr uint32_t kMaxWaitMs = 2000;
 constexpr int kWin = 32;                                  // time steps per staged input / logit window
 constexpr int kTileBytes = 128 * (kWin + 1) * 4;          // [128 frames][32 steps] fp32, padded rows
-constexpr uint32_t COL_D = 0, COL_A = 96;   // tensor-memory columns of a group: gates 0..4H-1, A operand 96..111
+constexpr uint32_t COL_D = 0, COL_A = kGroups == 4 ? 96 : 80;   // tensor-memory columns of a group: gates 0..4H-1, A operand 96..111
 
 struct LstmTcParams {
   const uint8_t* image;   // [enc B operand | dec B operand] bf16, canonical K-major, then lin_w[H], lin_b (fp32)
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
-  const uint32_t tmem_grp = tmem_base + g * 128;
+  const uint32_t tmem_grp = tmem_base + g * kGroupCols;
   const uint32_t tmem_d = tmem_grp + (static_cast<uint32_t>(wq * 32) << 16);
   constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, N);
 

@@ -8,7 +8,7 @@ from nvd import montecarlo, weights
 from oracle import lstm as olstm
 
 L, H = 100, 20
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 8
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 10   # two rounds of 5 groups per SM
 p = olstm.init_params(H, seed=4)
 with montecarlo.Simulator(0) as sim:
     h = sim.load_lstm(weights.LstmModel(**p))
