@@ -619,10 +619,21 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
   if (!ctx->copy_in) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
   if (!ctx->copy_out) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   const uint64_t frames = cfg->frames;
-  // 128 frames per tile, 4 tile streams per SM: slices of a whole number of waves keep the tail small
+  // 128 frames per tile, 4 tile streams per SM: slices of a whole number of waves keep the tails small.  The first
+  // copy-in and the last copy-out are the only transfers nothing overlaps, so the schedule starts and ends with
+  // short slices (4, 8 waves) around 24-wave ones.
   const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * 4 * 128;
-  uint64_t slice = std::max<uint64_t>(wave * 24, 1);
-  const size_t n_slices = static_cast<size_t>((frames + slice - 1) / slice);
+  std::vector<uint64_t> slices;
+  {
+    uint64_t left = frames;
+    auto take = [&](uint64_t waves) { const uint64_t n = std::min<uint64_t>(left, waves * wave); if (n) slices.push_back(n); left -= n; };
+    take(4);
+    take(8);
+    while (left > 32 * wave) take(24);
+    if (left > 8 * wave) take((left - 8 * wave + wave - 1) / wave);
+    take(8);
+  }
+  const size_t n_slices = slices.size();
   while (ctx->slice_ev.size() < 2 * n_slices + 1) {
     cudaEvent_t e;
     NVD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -639,9 +650,9 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
   NVD_CUDA(cudaEventRecord(ev_start, ctx->stream));
   NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_start, 0));
   NVD_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_start, 0));
-  size_t s = 0;
-  for (uint64_t off = 0; off < frames; off += slice, ++s) {
-    const uint64_t n = std::min<uint64_t>(slice, frames - off);
+  uint64_t off = 0;
+  for (size_t s = 0; s < n_slices; off += slices[s], ++s) {
+    const uint64_t n = slices[s];
     NVD_CUDA(cudaMemcpyAsync(d_info + off, info_host + off, n, cudaMemcpyHostToDevice, ctx->copy_in));
     NVD_CUDA(cudaEventRecord(ctx->slice_ev[2 * s], ctx->copy_in));
     NVD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->slice_ev[2 * s], 0));
