@@ -96,6 +96,13 @@ __device__ __forceinline__ void noise4(uint64_t seed, uint64_t frame, uint32_t b
   box_muller(x.z, x.w, z[2], z[3]);
 }
 
+__device__ __forceinline__ void noise4(const PhiloxKeys& rk, uint64_t frame, uint32_t block,
+                                       uint32_t stream_word, float z[4]) {
+  const uint4 x = frame_words(rk, frame, block, stream_word);
+  box_muller(x.x, x.y, z[0], z[1]);
+  box_muller(x.z, x.w, z[2], z[3]);
+}
+
 // 8 standard normals of symbols 4*block .. 4*block+7: the same arithmetic as two noise4 calls, written
 // stage by stage (both Philox chains, then all lg2, all sqrt, all sin/cos) so that the MUFU
 // operations of the four Box-Muller pairs are in flight together instead of queueing one by one.

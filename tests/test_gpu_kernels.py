@@ -124,7 +124,7 @@ def test_encoder_empty_and_linearity_at_scale(sim):
 
 # ------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("n,B,frame0,snr_idx", [(14, 4096, 0, 0), (14, 1001, 123456789012, 5), (200, 257, 7, 2),
-                                               (15, 333, 1, 1), (1036, 64, 0, 3)])
+                                               (15, 333, 1, 1), (1036, 64, 0, 3), (16, 500, 3, 1), (6, 77, 0, 0), (2, 33, 9, 4)])
 def test_channel_matches_oracle(sim, n, B, frame0, snr_idx):
     rng = np.random.default_rng(n + B)
     coded = rng.integers(0, 2, size=(B, n))
