@@ -245,6 +245,31 @@ def main():
         staged["total_ms"] = sum(ms.values())
         staged["gbit_per_s"] = frames * L / (staged["total_ms"] * 1e-3) / 1e9
 
+    # ---------------- BASELINE.json configs[3]: rnn_viterbi LSTM seq2seq, (133,171) L = 100 blocks (K4-tc) -----------
+    other = None
+    if not args.no_staged and world == 1:
+        from nvd import weights as _w, _lib as _l
+        Hh, Ll, Bl = 20, 100, info["sm_count"] * 5 * 128
+        rng = np.random.default_rng(4)
+        lim = float(np.sqrt(6.0 / (1 + Hh + 4 * Hh)))
+        lp = {"enc_W": rng.uniform(-lim, lim, (1 + Hh, 4 * Hh)), "enc_b": np.zeros(4 * Hh), "dec_W": rng.uniform(-lim, lim, (1 + Hh, 4 * Hh)),
+              "dec_b": np.zeros(4 * Hh), "lin_w": rng.uniform(-0.5, 0.5, Hh), "lin_b": np.zeros(1)}
+        hl = sim.load_lstm(_w.LstmModel(**{k: v.astype(np.float32) for k, v in lp.items()}))
+        d_y = sim.to_device(rng.standard_normal((Bl, 2 * Ll)).astype(np.float32))
+        d_hard = sim.alloc(Bl * 25)
+        def lstm_step(mode):
+            _l.check(sim.lib.nvd_lstm_forward(sim.ctx, hl, d_y.ptr, _l.DTYPES["f32"], None, 2 * Ll, 2 * Ll, Bl, mode, None, d_hard.ptr))
+        other = {"workload": "configs[3]: rnn_viterbi LSTM(20) seq2seq, L=100 (T=200+200), autoregressive decisions", "frames": Bl}
+        for name, mode, reps in (("fp32_pipe", 1, 2), ("tcgen05_bf16", 2, 10)):
+            lstm_step(mode); sim.sync()
+            e0, e1 = sim.event(), sim.event()
+            sim.record(e0)
+            for _ in range(reps):
+                lstm_step(mode)
+            sim.record(e1); sim.sync()
+            ms_l = sim.elapsed_ms(e0, e1) / reps
+            other[name] = {"ms": ms_l, "gbit_per_s": Bl * Ll / (ms_l * 1e-3) / 1e9, "mframes_per_s": Bl / (ms_l * 1e-3) / 1e6}
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
@@ -290,6 +315,7 @@ def main():
         "ber": ber, "frame_errors": int(total_counts[0, 1]), "frames_total": int(total_counts[0, 2]),
         "allreduce_ms": ar_ms,
         "staged": staged,
+        "rnn_viterbi": other,
         "e2e_counters": [int(x) for x in c_e2e],
     }
     print(json.dumps(line), flush=True)
