@@ -113,10 +113,20 @@ int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts,
 int nvd_mlp_free(nvd_ctx* ctx, int model);
 /* y: [B, dims[0]] in y_dtype.  soft_out: [B, dims[n]] fp32 or NULL.  hard_out: argmax class
  * (first index on ties) as hard_bytes-wide (1, 2 or 4) little-endian integers, or NULL.
- * NVD_PREC_BF16_TC needs a tcgen05-covered shape (see nvd_mlp_tc_supported). */
+ * NVD_PREC_BF16_TC needs a tcgen05-covered shape (see nvd_mlp_tc_supported): the reference FNN 14-128-64-32-128
+ * runs on the fused single-kernel path (y must be NVD_BF16); any other model whose layer widths are <= 511 with
+ * <= 128 classes runs layer by layer on the wide-layer tensor-core kernel (y in any dtype). */
 int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t B, int precision,
                     float* soft_out, void* hard_out, int hard_bytes);
 int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported);
+/* Sliding-window decode (src/fnn_viterbi_seq_predict.py:293-336 get_single_instance + the forward of :343-414):
+ * window i = stream[i * stride, i * stride + dims[0]) of one long symbol stream in device memory
+ * (stream_dtype NVD_F32 / NVD_BF16 / NVD_I32_TRUNC), i < n_windows; soft_out [n_windows, n_out] fp32 or NULL,
+ * hard_out class index per window or NULL.  NVD_PREC_BF16_TC needs the wide-layer tensor-core image (all layer
+ * widths <= 511, <= 128 classes; nvd_mlp_tc_supported), NVD_PREC_FP32 accepts any model.  Asynchronous. */
+int nvd_window_decode(nvd_ctx* ctx, int model, const void* stream, int stream_dtype, int64_t n_symbols,
+                      int64_t stride, int64_t n_windows, int precision, float* soft_out, void* hard_out,
+                      int hard_bytes);
 /* How the tensor-core path evaluates the hidden-layer tanh (so a numerical model can follow it exactly):
  * of every 8 consecutive bf16 pairs (16 columns) of a layer, the first *poly_pairs_of_8 use
  *   tanh(x) ~ sign(x) * u * (c[0] + c[1] u + ... + c[5] u^5),  u = min(|x| * *inv_range, 1)   (fp32, FMA pipe)

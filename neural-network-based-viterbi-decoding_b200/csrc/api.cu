@@ -51,6 +51,17 @@ static float sigma_of_db(float snr_db) {
   return static_cast<float>(std::sqrt(0.5 / std::pow(10.0, static_cast<double>(snr_db) / 10.0)));
 }
 
+// overlapping windows of a stream as dense fp32 rows (the fp32 parity path of nvd_window_decode)
+template <typename T>
+__global__ void gather_windows_f32_kernel(const T* __restrict__ src, int64_t src_len, int64_t stride, int K, int64_t B,
+                                          float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= B * K) return;
+  const int64_t row = i / K;
+  const int64_t s = row * stride + (i - row * K);
+  out[i] = s < src_len ? static_cast<float>(src[s]) : 0.0f;
+}
+
 }  // namespace nvd
 
 using namespace nvd;
@@ -123,6 +134,7 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
     for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m.W[l]); cudaFree(m.b[l]); }
     cudaFree(m.tc_image);
     cudaFree(m.tc_bias_out);
+    for (int l = 0; l < kMaxLayers; ++l) cudaFree(m.wide_image[l]);
   }
   for (auto& m : ctx->lstms) { cudaFree(m.blob); cudaFree(m.tc_image); }
   cudaFree(ctx->scratch);
@@ -331,6 +343,7 @@ int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts, c
     NVD_CUDA(cudaMemcpy(m.b[l], b_host[l], dims[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (tc_shape_supported(m)) NVD_TRY(tc_build_image(ctx, m, W_host, b_host));
+  else if (wide_tc_supported(m)) NVD_TRY(wide_tc_build_image(m, W_host, b_host));
   ctx->mlps.push_back(m);
   *model = static_cast<int>(ctx->mlps.size()) - 1;
   return NVD_OK;
@@ -350,6 +363,8 @@ int nvd_mlp_free(nvd_ctx* ctx, int model) {
   for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->W[l]); cudaFree(m->b[l]); m->W[l] = m->b[l] = nullptr; }
   cudaFree(m->tc_image); m->tc_image = nullptr;
   cudaFree(m->tc_bias_out); m->tc_bias_out = nullptr;
+  for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->wide_image[l]); m->wide_image[l] = nullptr; }
+  m->wide = false;
   m->live = false;
   return NVD_OK;
 }
@@ -358,7 +373,64 @@ int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported) {
   NVD_REQUIRE(ctx && supported, "null argument");
   MlpModel* m;
   NVD_TRY(get_mlp(ctx, model, &m));
-  *supported = m->tc_image ? 1 : 0;
+  *supported = (m->tc_image || m->wide) ? 1 : 0;
+  return NVD_OK;
+}
+
+// wide-layer tensor-core path over `B` rows starting every `row_stride` elements of `src`, in passes that bound the
+// activation scratch
+static int wide_rows(nvd_ctx* ctx, const MlpModel& m, const void* src, int src_dtype, int64_t src_len, int64_t row_stride,
+                     int64_t B, float* soft_out, void* hard_out, int hard_bytes) {
+  const int64_t pass = std::min<int64_t>(B, int64_t(1) << 18);
+  NVD_TRY(ensure_scratch(ctx, wide_tc_scratch_bytes(m, pass)));
+  const size_t esz = src_dtype == NVD_BF16 ? 2 : 4;
+  const int n_out = m.dims[m.n_layers];
+  for (int64_t r0 = 0; r0 < B; r0 += pass) {
+    const int64_t n = std::min(pass, B - r0);
+    const char* s0 = static_cast<const char*>(src) + static_cast<size_t>(r0 * row_stride) * esz;
+    NVD_TRY(launch_mlp_wide_tc(ctx, m, s0, src_dtype, src_len - r0 * row_stride, row_stride, n, ctx->scratch,
+                               soft_out ? soft_out + r0 * n_out : nullptr,
+                               hard_out ? static_cast<char*>(hard_out) + r0 * hard_bytes : nullptr, hard_bytes));
+  }
+  return NVD_OK;
+}
+
+static int ensure_mc_buf(nvd_ctx* ctx, size_t bytes);
+
+int nvd_window_decode(nvd_ctx* ctx, int model, const void* stream, int stream_dtype, int64_t n_symbols, int64_t stride,
+                      int64_t n_windows, int precision, float* soft_out, void* hard_out, int hard_bytes) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  NVD_REQUIRE(stream && n_symbols >= 0 && stride >= 1 && n_windows >= 0, "bad stream / stride / window count");
+  NVD_REQUIRE(stream_dtype == NVD_F32 || stream_dtype == NVD_BF16 || stream_dtype == NVD_I32_TRUNC, "unknown stream dtype %d", stream_dtype);
+  NVD_REQUIRE(!hard_out || hard_bytes == 1 || hard_bytes == 2 || hard_bytes == 4, "hard_bytes must be 1, 2 or 4");
+  const int K = m->dims[0];
+  NVD_REQUIRE(n_windows == 0 || (n_windows - 1) * stride + K <= n_symbols, "windows run past the end of the stream");
+  if (n_windows == 0) return NVD_OK;
+  if (precision == NVD_PREC_BF16_TC) {
+    if (!m->wide) { set_error("model %d has no wide-layer tensor-core image", model); return NVD_ERR_UNSUPPORTED; }
+    return wide_rows(ctx, *m, stream, stream_dtype, n_symbols, stride, n_windows, soft_out, hard_out, hard_bytes);
+  }
+  NVD_REQUIRE(precision == NVD_PREC_FP32, "unknown precision %d", precision);
+  const int64_t pass = std::min<int64_t>(n_windows, int64_t(1) << 18);
+  const int n_out = m->dims[m->n_layers];
+  const size_t esz = stream_dtype == NVD_BF16 ? 2 : 4;
+  for (int64_t r0 = 0; r0 < n_windows; r0 += pass) {
+    const int64_t n = std::min(pass, n_windows - r0);
+    // the fp32 layer kernel uses ctx->scratch itself: the gathered windows live in the Monte-Carlo buffer
+    NVD_TRY(ensure_mc_buf(ctx, static_cast<size_t>(pass) * K * 4));
+    float* win = static_cast<float*>(ctx->mc_buf);
+    const char* s0 = static_cast<const char*>(stream) + static_cast<size_t>(r0 * stride) * esz;
+    const int64_t len = n_symbols - r0 * stride;
+    const unsigned grid = static_cast<unsigned>((n * K + 255) / 256);
+    if (stream_dtype == NVD_F32) gather_windows_f32_kernel<float><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(s0), len, stride, K, n, win);
+    else if (stream_dtype == NVD_BF16) gather_windows_f32_kernel<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16*>(s0), len, stride, K, n, win);
+    else gather_windows_f32_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const int32_t*>(s0), len, stride, K, n, win);
+    NVD_CHECK_LAUNCH();
+    NVD_TRY(launch_mlp_fp32(ctx, *m, win, NVD_F32, n, soft_out ? soft_out + r0 * n_out : nullptr,
+                            hard_out ? static_cast<char*>(hard_out) + r0 * hard_bytes : nullptr, hard_bytes));
+  }
   return NVD_OK;
 }
 
@@ -373,6 +445,7 @@ int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t
   NVD_REQUIRE(!hard_out || hard_bytes == 4 || m->dims[m->n_layers] <= (1 << (8 * hard_bytes)), "class index does not fit hard_bytes");
   if (precision == NVD_PREC_FP32) return launch_mlp_fp32(ctx, *m, y, y_dtype, B, soft_out, hard_out, hard_bytes);
   if (precision == NVD_PREC_BF16_TC) {
+    if (m->wide) return wide_rows(ctx, *m, y, y_dtype, B * m->dims[0], m->dims[0], B, soft_out, hard_out, hard_bytes);
     if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
     NVD_REQUIRE(y_dtype == NVD_BF16, "BF16_TC path takes bf16 inputs (TMA-staged activations)");
     return launch_mlp_tc_staged(ctx, *m, static_cast<const __nv_bfloat16*>(y), B, soft_out, hard_out, hard_bytes);

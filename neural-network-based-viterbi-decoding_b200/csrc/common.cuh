@@ -58,6 +58,9 @@ struct MlpModel {
   // bias rows folded in (k3_mlp_tc.cu); nullptr when the shape is not covered.
   void* tc_image = nullptr;
   size_t tc_image_bytes = 0;
+  // layer-per-launch tensor-core path for wide layers (k_mlp_wide_tc.cu): one bf16 image per layer
+  bool wide = false;
+  void* wide_image[kMaxLayers] = {nullptr};
   float* tc_bias_out = nullptr;  // reserved
   float tc_out_offset = 0.0f;    // power of two added to the output accumulators (positive-key argmax)
 };
@@ -116,6 +119,13 @@ int launch_count(nvd_ctx* ctx, const void* pred, const void* label, int stride, 
                  int flags, uint64_t* counters);
 int launch_lstm(nvd_ctx* ctx, const LstmModel& m, const void* y, int y_dtype, const float* dec_in,
                 int T_enc, int T_dec, int64_t B, int fast_math, float* logits, uint8_t* hard);
+
+// wide-layer tensor-core path (k_mlp_wide_tc.cu): widths <= 511, output <= 128 classes
+bool wide_tc_supported(const MlpModel& m);
+int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* const* b_host);
+size_t wide_tc_scratch_bytes(const MlpModel& m, int64_t rows);
+int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src_dtype, int64_t src_len, int64_t row_stride,
+                       int64_t B, void* scratch, float* soft_out, void* hard_out, int hard_bytes);
 
 // tensor-core recurrence (k_lstm_tc.cu)
 bool lstm_tc_supported(int H);

@@ -1,0 +1,359 @@
+// K3-wide: feed-forward decoders whose layers are too wide to keep every weight in shared memory —
+// the sliding-window decoder 200 -> 500 -> 500 -> 500 -> 500 -> 2 of
+// /root/reference/src/fnn_viterbi_seq_predict.py:343-414 (tanh after every affine, :408-412; 851 000 MAC per
+// decoded bit) and any other MLP with layer widths <= 511 — on the tensor core, ONE LAYER PER LAUNCH:
+//     Y[128 x N] = act( X[128 x K] W[K x N] + b ),  bf16 x bf16 -> fp32 accumulate, bf16 activations between layers.
+// Per CTA (persistent, one per SM) and 128-row tile:
+//   * the tile's X rows go HBM -> registers -> TENSOR memory (tcgen05.st, two K elements per column): the A operand
+//     of every MMA of the tile comes from TMEM (TS mode), so shared memory carries only the weights;
+//   * W streams from L2 through a ring of 16 KB shared-memory stages ([<=128 n-rows] x [64 k]) filled by a producer
+//     warp with 1-D TMA bulk copies (the host pre-arranges W in the UMMA canonical K-major layout, chunked by 128
+//     output columns, so every stage is one contiguous copy) and handed over with full/empty mbarriers;
+//   * one issuer thread runs the K loop (4 MMAs per stage) into one of two 128-column accumulators; the four
+//     epilogue warps (thread r = row r = TMEM lane r) read the other one, apply the activation and write bf16 rows
+//     of the next layer's input, so the epilogue of chunk c overlaps the MMAs of chunk c+1;
+//   * biases ride in the contraction: every X row carries 1.0 at column K (the previous layer's epilogue gets it
+//     from a weight trick: bias row of that padding column = 20 -> tanh = 1, or 1 for relu / identity).
+// The last layer's epilogue takes the argmax (first index on ties) and optional fp32 soft outputs.
+// Row gathering (dense rows, or overlapping stride-2 windows of one long stream: get_single_instance,
+// fnn_viterbi_seq_predict.py:293-336) is a small pad/convert kernel in front of the first layer.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nvd {
+
+namespace {
+
+constexpr int kThreads = 192;            // warps 0-3: rows / epilogue, warp 4: weight producer, warp 5: MMA issuer
+constexpr int kStages = 6;
+constexpr int kStageK = 64;              // k extent of one stage
+constexpr int kStageBytes = 128 * kStageK * 2;   // 16 KB (a full 128-column chunk)
+constexpr int kMaxKp = 512;
+constexpr uint32_t COL_A = 256;          // A operand: columns 256 .. 256 + Kp/2; accumulators: 0..127 and 128..255
+constexpr uint32_t kMaxWaitMs = 4000;
+
+struct WideParams {
+  const __nv_bfloat16* X;   // [B, Kp] rows, 1.0 at column K
+  const uint8_t* W;         // image: per 128-column chunk [Kp/8][Nc][8] bf16
+  void* Y;                  // hidden: bf16 [B, Np] ; last: unused
+  float* soft;              // last layer: fp32 [B, N] or null
+  void* hard;               // last layer: class index or null
+  int hard_bytes;
+  int64_t B;
+  int Kp, N, Np;            // padded K, true N, padded N (hidden: next layer's Kp; last: round_up(N, 16))
+  int act;
+  int last;
+  int* abort_flag;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == NVD_ACT_TANH) return ptx::tanh_approx(v);
+  if (act == NVD_ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  constexpr int BAR_OFF = kStages * kStageBytes;
+  const uint32_t bar_full = sbase + BAR_OFF;                 // [kStages]
+  const uint32_t bar_empty = sbase + BAR_OFF + 8 * kStages;  // [kStages]
+  const uint32_t bar_dfull = sbase + BAR_OFF + 16 * kStages;        // [2]
+  const uint32_t bar_dfree = sbase + BAR_OFF + 16 * kStages + 16;   // [2]
+  const uint32_t bar_aready = sbase + BAR_OFF + 16 * kStages + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * kStages + 48);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar_dfull + 8 * b, 1); ptx::mbar_init(bar_dfree + 8 * b, 4); }
+    ptx::mbar_init(bar_aready, 4);
+    ptx::mbar_fence_init();
+  }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+
+  const int64_t num_tiles = (p.B + 127) >> 7;
+  const int n_chunks = (p.Np + 127) >> 7;
+  const int k_stages = p.Kp / kStageK;
+  auto chunk_cols = [&](int c) { return min(128, p.Np - 128 * c); };
+
+  if (warp == 4) {
+    // ---- weight producer: the whole image once per tile, stage by stage ----------------------------------
+    if (ptx::elect_one()) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        size_t off = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+          const uint32_t bytes = static_cast<uint32_t>(chunk_cols(c)) * kStageK * 2;
+          for (int ks = 0; ks < k_stages; ++ks, ++it, off += bytes) {
+            const int s = it % kStages;
+            if (!ptx::mbar_wait_bounded(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 30); return; }
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+            ptx::bulk_g2s(sbase + s * kStageBytes, p.W + off, bytes, bar_full + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer -------------------------------------------------------------------------------------
+    if (ptx::elect_one()) {
+      uint32_t it = 0, tile_it = 0, chunk_it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        if (!ptx::mbar_wait_bounded(bar_aready, tile_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 31); return; }
+        ptx::tc_fence_after();
+        for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
+          const int buf = chunk_it & 1;
+          const int nc = chunk_cols(c);
+          if (!ptx::mbar_wait_bounded(bar_dfree + 8 * buf, ((chunk_it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 32); return; }
+          ptx::tc_fence_after();
+          const uint32_t idesc = ptx::make_idesc_bf16_f32(128, nc);
+          for (int ks = 0; ks < k_stages; ++ks, ++it) {
+            const int s = it % kStages;
+            if (!ptx::mbar_wait_bounded(bar_full + 8 * s, (it / kStages) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 33); return; }
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kStageK / 16; ++j)
+              ptx::umma_f16_ts(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
+                               ptx::make_smem_desc(sbase + s * kStageBytes + j * 2 * (nc * 16), nc * 16, 128), idesc,
+                               (ks | j) != 0);
+            ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
+          }
+          ptx::umma_commit(bar_dfull + 8 * buf);           // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ---- rows: load X into tensor memory, epilogues --------------------------------------------------------
+    const int r = tid;                                     // 0..127
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t chunk_it = 0;
+    auto load_rows = [&](int64_t tile) {
+      const int64_t row = tile * 128 + r;
+      const uint4* src = reinterpret_cast<const uint4*>(p.X + row * p.Kp);
+      for (int c = 0; c < p.Kp / 32; ++c) {               // 32 bf16 = 16 columns per step
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 v = row < p.B ? __ldg(src + 4 * c + q) : make_uint4(0u, 0u, 0u, 0u);
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        ptx::tmem_st16(tmem_base + lane_base + COL_A + 16 * c, w);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) ptx::mbar_arrive(bar_aready);
+    };
+    auto epilogue = [&](int64_t tile, int c, int buf) {
+      const int64_t row = tile * 128 + r;
+      const int nc = chunk_cols(c);
+      const uint32_t d = tmem_base + lane_base + 128 * buf;
+      if (!p.last) {
+        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.Y) + row * p.Np + 128 * c;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(d + c0, v);
+          ptx::tmem_wait_ld();
+          if (row < p.B) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c0 + 8 * q < nc) {
+                uint4 o;
+                o.x = pack_bf16x2(apply_act(__uint_as_float(v[8 * q]), p.act), apply_act(__uint_as_float(v[8 * q + 1]), p.act));
+                o.y = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 2]), p.act), apply_act(__uint_as_float(v[8 * q + 3]), p.act));
+                o.z = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 4]), p.act), apply_act(__uint_as_float(v[8 * q + 5]), p.act));
+                o.w = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 6]), p.act), apply_act(__uint_as_float(v[8 * q + 7]), p.act));
+                *reinterpret_cast<uint4*>(out + c0 + 8 * q) = o;
+              }
+            }
+          }
+        }
+      } else {
+        // output layer (N <= 128 classes in one chunk): argmax on the pre-activation (monotone activations), soft outputs
+        float best = -3.0e38f;
+        int bi = 0;
+        for (int c0 = 0; c0 < nc; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(d + c0, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = 128 * c + c0 + j;
+            const float z = __uint_as_float(v[j]);
+            if (col < p.N) {
+              if (z > best) { best = z; bi = col; }
+              if (p.soft != nullptr && row < p.B) p.soft[row * p.N + col] = (p.act == NVD_ACT_TANH) ? tanhf(z) : apply_act(z, p.act);
+            }
+          }
+        }
+        if (p.hard != nullptr && row < p.B) {
+          if (p.act == NVD_ACT_RELU && best <= 0.0f) bi = 0;    // relu ties at (0, ..., 0) -> class 0 (first index)
+          if (p.hard_bytes == 1) static_cast<uint8_t*>(p.hard)[row] = static_cast<uint8_t>(bi);
+          else if (p.hard_bytes == 2) static_cast<uint16_t*>(p.hard)[row] = static_cast<uint16_t>(bi);
+          else static_cast<int32_t*>(p.hard)[row] = bi;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) ptx::mbar_arrive(bar_dfree + 8 * buf);
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tile < num_tiles) load_rows(tile);
+    for (; tile < num_tiles; tile += gridDim.x) {
+      for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
+        const int buf = chunk_it & 1;
+        if (!ptx::mbar_wait_bounded(bar_dfull + 8 * buf, (chunk_it >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 34); goto done; }
+        ptx::tc_fence_after();
+        // the last accumulator of the tile is complete => every MMA of the tile has read its A operand: bring the
+        // next tile's rows in first, so that its MMAs run under this epilogue
+        if (c == n_chunks - 1 && tile + gridDim.x < num_tiles) load_rows(tile + gridDim.x);
+        epilogue(tile, c, buf);
+      }
+    }
+  }
+done:
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// rows of the first layer: dense ([B, K] with row stride K) or overlapping windows of one stream (row stride =
+// window stride, e.g. 2), converted to bf16, 1.0 at column K, zero padding up to Kp
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, int64_t src_len, int64_t row_stride, int K, int Kp, int64_t B,
+                                   __nv_bfloat16* __restrict__ X) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // one thread = 8 output columns
+  const int per_row = Kp / 8;
+  const int64_t row = i / per_row;
+  if (row >= B) return;
+  const int c0 = static_cast<int>(i - row * per_row) * 8;
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = c0 + j;
+    float f = 0.0f;
+    if (col < K) { const int64_t s = row * row_stride + col; f = s < src_len ? static_cast<float>(src[s]) : 0.0f; }
+    else if (col == K) f = 1.0f;
+    v[j] = __float2bfloat16_rn(f);
+  }
+  *reinterpret_cast<uint4*>(X + row * Kp + c0) = *reinterpret_cast<const uint4*>(v);
+}
+
+uint16_t bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+bool wide_tc_supported(const MlpModel& m) {
+  for (int l = 0; l <= m.n_layers; ++l)
+    if (m.dims[l] + 1 > kMaxKp) return false;
+  if (m.dims[m.n_layers] > 128) return false;   // output layer: one accumulator chunk
+  return true;
+}
+
+// image of layer l: Kp = round_up(K + 1, 64) rows (row K = bias), Np columns (hidden: next layer's Kp, column N is
+// the next layer's bias column: its bias-row entry makes act(.) = 1; last: round_up(N, 16)); chunked by 128 columns,
+// each chunk [Kp/8][Nc][8] bf16 (UMMA canonical K-major, no swizzle)
+int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* const* b_host) {
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int K = m.dims[l], N = m.dims[l + 1];
+    const int Kp = round_up(K + 1, 64);
+    const bool last = l == m.n_layers - 1;
+    const int Np = last ? round_up(N, 16) : round_up(N + 1, 64);
+    std::vector<uint16_t> img(static_cast<size_t>(Kp) * Np, 0);
+    size_t chunk_off = 0;
+    for (int c = 0; c * 128 < Np; ++c) {
+      const int nc = std::min(128, Np - 128 * c);
+      for (int nn = 0; nn < nc; ++nn) {
+        const int n = 128 * c + nn;
+        for (int k = 0; k < Kp; ++k) {
+          float v = 0.0f;
+          if (n < N) {
+            if (k < K) v = W_host[l][static_cast<size_t>(k) * N + n];
+            else if (k == K) v = b_host[l][n];
+          } else if (!last && n == N && k == K) {
+            v = (m.acts[l] == NVD_ACT_TANH) ? 20.0f : 1.0f;     // the next layer's constant-one column
+          }
+          img[chunk_off + static_cast<size_t>(k >> 3) * (nc * 8) + nn * 8 + (k & 7)] = bf16_rn(v);
+        }
+      }
+      chunk_off += static_cast<size_t>(Kp) * nc;
+    }
+    NVD_CUDA(cudaMalloc(&m.wide_image[l], img.size() * 2));
+    NVD_CUDA(cudaMemcpy(m.wide_image[l], img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+  m.wide = true;
+  return NVD_OK;
+}
+
+size_t wide_tc_scratch_bytes(const MlpModel& m, int64_t rows) {
+  int widest = 0;
+  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 64));
+  return 2 * static_cast<size_t>(rows) * widest * 2 + 512;
+}
+
+// rows: `B` rows taken from `src` (dtype NVD_F32 / NVD_BF16 / NVD_I32_TRUNC) at element stride `row_stride`
+// (dims[0] for dense rows), `src_len` elements long.  scratch: wide_tc_scratch_bytes(m, B) bytes.
+int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src_dtype, int64_t src_len, int64_t row_stride,
+                       int64_t B, void* scratch, float* soft_out, void* hard_out, int hard_bytes) {
+  if (B == 0) return NVD_OK;
+  int widest = 0;
+  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 64));
+  __nv_bfloat16* ping = static_cast<__nv_bfloat16*>(scratch);
+  __nv_bfloat16* pong = ping + static_cast<size_t>(B) * widest;
+  const int K0 = m.dims[0], Kp0 = round_up(K0 + 1, 64);
+  {
+    const int64_t threads = B * (Kp0 / 8);
+    const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
+    if (src_dtype == NVD_F32) gather_rows_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(src), src_len, row_stride, K0, Kp0, B, ping);
+    else if (src_dtype == NVD_BF16) gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(src), src_len, row_stride, K0, Kp0, B, ping);
+    else gather_rows_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(src), src_len, row_stride, K0, Kp0, B, ping);
+    NVD_CHECK_LAUNCH();
+  }
+  const int smem = kStages * kStageBytes + 256;
+  NVD_CUDA(cudaFuncSetAttribute(mlp_wide_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (B + 127) / 128;
+  const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles));
+  for (int l = 0; l < m.n_layers; ++l) {
+    WideParams p{};
+    const bool last = l == m.n_layers - 1;
+    p.X = ping;
+    p.W = static_cast<const uint8_t*>(m.wide_image[l]);
+    p.Y = pong;
+    p.soft = last ? soft_out : nullptr;
+    p.hard = last ? hard_out : nullptr;
+    p.hard_bytes = hard_bytes;
+    p.B = B;
+    p.Kp = round_up(m.dims[l] + 1, 64);
+    p.N = m.dims[l + 1];
+    p.Np = last ? round_up(p.N, 16) : round_up(p.N + 1, 64);
+    p.act = m.acts[l];
+    p.last = last ? 1 : 0;
+    p.abort_flag = ctx->abort_flag;
+    mlp_wide_layer_kernel<<<grid, kThreads, smem, ctx->stream>>>(p);
+    NVD_CHECK_LAUNCH();
+    std::swap(ping, pong);
+  }
+  return NVD_OK;
+}
+
+}  // namespace nvd

@@ -65,6 +65,7 @@ _PROTOS = {
     "nvd_mlp_free": ([_vp, _i], _i),
     "nvd_mlp_forward": ([_vp, _i, _vp, _i, _i64, _i, _vp, _vp, _i], _i),
     "nvd_mlp_tc_supported": ([_vp, _i, C.POINTER(_i)], _i),
+    "nvd_window_decode": ([_vp, _i, _vp, _i, _i64, _i64, _i64, _i, _vp, _vp, _i], _i),
     "nvd_tc_tanh_model": ([C.POINTER(_i), C.POINTER(_f), C.POINTER(_f)], _i),
     "nvd_mlp_decode_host": ([_vp, _i, _vp, _i64, _i, _vp, _vp], _i),
     "nvd_lstm_load": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)], _i),

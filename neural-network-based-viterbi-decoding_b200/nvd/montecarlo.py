@@ -222,6 +222,15 @@ class Simulator:
                      counters: DeviceBuffer):
         check(self.lib.nvd_count_errors(self.ctx, pred.ptr, label.ptr, stride, L, B, flags, counters.ptr))
 
+    def window_decode(self, h: int, stream: DeviceBuffer, stream_dtype, n_symbols: int, stride: int, n_windows: int,
+                      n_out: int, precision="fp32", want_soft=True, hard_bytes=4):
+        """Sliding-window decode of one long symbol stream in device memory (nvd_window_decode)."""
+        soft = self.alloc(n_windows * n_out * 4) if want_soft else None
+        hard = self.alloc(n_windows * hard_bytes)
+        check(self.lib.nvd_window_decode(self.ctx, h, stream.ptr, _lib.DTYPES[stream_dtype], n_symbols, stride, n_windows,
+                                         _lib.PRECISIONS[precision], soft.ptr if soft else None, hard.ptr, hard_bytes))
+        return soft, hard
+
     def lstm_forward(self, h: int, y: DeviceBuffer, y_dtype, dec_in, T_enc: int, T_dec: int, B: int, fast_math=False,
                      want_logits=True, want_hard=True):
         logits = self.alloc(B * T_dec * 4) if want_logits else None

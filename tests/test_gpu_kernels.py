@@ -324,3 +324,59 @@ def test_lstm_tensor_core_recurrence(sim, H, B):
     ha = np.unpackbits(hard_a.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
     hr = np.unpackbits(hard_r.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
     assert (ha == hr).all(axis=1).mean() > 0.9            # a flipped near-zero logit changes the fed-back path
+
+
+# ------------------------------------------------------------------------------------------ K3-wide
+@pytest.mark.parametrize("dims,acts,B", [([200, 500, 500, 500, 500, 2], [1, 1, 1, 1, 1], 1000),   # seq_predict (:343-414)
+                                         ([200, 500, 500, 500, 500, 2], [1, 1, 1, 1, 1], 148 * 128 + 5),
+                                         ([30, 64, 10], [2, 0], 129),                             # relu hidden, identity out
+                                         ([17, 129, 70, 128], [1, 2, 1], 300),                    # chunk tails, 128 classes
+                                         ([14, 20], [1], 77)])
+def test_mlp_wide_tensor_core_matches_oracle(sim, dims, acts, B):
+    """Layer-per-launch tcgen05 path (A operand in tensor memory, weights streamed through a TMA ring) against the
+    fp64 oracle and the bf16 numerical model, inputs in fp32 (converted on the device)."""
+    m = _model(dims, acts, seed=len(dims) + dims[1], bias=0.1)
+    h = sim.load_mlp(m)
+    assert sim.mlp_tc_supported(h)
+    rng = np.random.default_rng(B)
+    y = rng.standard_normal((B, dims[0])).astype(np.float32)
+    soft_b, hard_b = sim.mlp_forward(h, sim.to_device(y), "f32", B, dims[-1], "bf16", want_soft=True, hard_bytes=4)
+    soft = soft_b.download(np.float32, (B, dims[-1]))
+    pred = hard_b.download(np.int32, (B,))
+    from nvd import montecarlo as mc
+    yq = mc.bf16_to_f32(mc.f32_to_bf16(y))
+    want64 = omlp.forward(yq, m.Ws, m.bs, m.acts, dtype=np.float64)
+    model16, _ = omlp.forward_bf16_model(yq, m.Ws, m.bs, m.acts)
+    scale = max(1.0, float(np.abs(want64).max()))
+    assert np.abs(soft - want64).max() <= 2e-2 * scale                # north-star bf16 tolerance
+    assert np.abs(soft - model16).max() <= 1e-2 * scale               # bf16 numerical model (bf16 bias as well)
+    ok = omlp.top2_margin(want64) >= 5e-2 * scale
+    assert (pred[ok] == omlp.argmax_first(want64)[ok]).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_window_decode_matches_dense_rows(sim, precision):
+    """nvd_window_decode over a stride-2 stream == the same windows decoded as dense rows (get_single_instance,
+    fnn_viterbi_seq_predict.py:293-336), both precisions, fp32 and int32-truncated streams."""
+    dims, acts = [200, 500, 500, 500, 500, 2], [1, 1, 1, 1, 1]
+    m = _model(dims, acts, seed=3, bias=0.05)
+    h = sim.load_mlp(m)
+    rng = np.random.default_rng(0)
+    n_win = 3000
+    n_sym = 2 * (n_win - 1) + 200
+    for dtype, arr in (("f32", rng.standard_normal(n_sym).astype(np.float32)),
+                       ("i32_trunc", rng.integers(-3, 4, n_sym).astype(np.int32))):
+        d_stream = sim.to_device(arr)
+        soft_b, hard_b = sim.window_decode(h, d_stream, dtype, n_sym, 2, n_win, 2, precision)
+        soft = soft_b.download(np.float32, (n_win, 2))
+        hard = hard_b.download(np.int32, (n_win,))
+        rows = np.lib.stride_tricks.sliding_window_view(arr.astype(np.float32), 200)[::2][:n_win]
+        s2_b, h2_b = sim.mlp_forward(h, sim.to_device(np.ascontiguousarray(rows)), "f32", n_win, 2, precision, want_soft=True, hard_bytes=4)
+        assert np.array_equal(soft, s2_b.download(np.float32, (n_win, 2)))
+        assert np.array_equal(hard, h2_b.download(np.int32, (n_win,)))
+        want = omlp.forward(rows, m.Ws, m.bs, m.acts, dtype=np.float64)
+        tol = 1e-5 if precision == "fp32" else 2e-2
+        assert np.abs(soft - want).max() <= tol
+    from nvd import NvdError
+    with pytest.raises(NvdError):
+        sim.window_decode(h, d_stream, "f32", n_sym, 2, n_win + 1, 2, precision)   # runs past the end of the stream
