@@ -18,6 +18,7 @@
 // Row gathering (dense rows, or overlapping stride-2 windows of one long stream: get_single_instance,
 // fnn_viterbi_seq_predict.py:293-336) is a small pad/convert kernel in front of the first layer.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -27,8 +28,8 @@ namespace nvd {
 
 namespace {
 
-constexpr int kThreads = 192;            // warps 0-3: rows / epilogue, warp 4: weight producer, warp 5: MMA issuer
-constexpr int kStages = 6;
+constexpr int kThreads = 320;            // warps 0-7: rows / epilogues (two sets of four), warp 8: weight producer, warp 9: MMA issuer
+constexpr int kStages = 6;              // 96 KB of weights in flight (13 stages measured no faster: not the bound)
 constexpr int kStageK = 64;              // k extent of one stage
 constexpr int kStageBytes = 128 * kStageK * 2;   // 16 KB (a full 128-column chunk)
 constexpr int kMaxKp = 512;
@@ -60,6 +61,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// CLUSTER CTAs (1, 2 or 4) share every weight stage: each loads 1/CLUSTER of it and multicasts that part to all, so
+// the L2 -> SM weight traffic (the bound of this kernel: the whole layer image per 128-row tile) drops by CLUSTER.
+// A stage is reusable once the MMAs of ALL CTAs have read it: every issuer commits to every CTA's empty barrier.
+template <int CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -74,23 +79,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * kStages + 48);
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, CLUSTER); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar_dfull + 8 * b, 1); ptx::mbar_init(bar_dfree + 8 * b, 4); }
-    ptx::mbar_init(bar_aready, 4);
+    ptx::mbar_init(bar_aready, 8);
     ptx::mbar_fence_init();
   }
   if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();     // barriers initialised cluster-wide before any multicast / remote arrival
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+  const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CLUSTER) - 1u);
 
-  const int64_t num_tiles = (p.B + 127) >> 7;
+  // every CTA of a cluster must walk the same number of tiles (they consume one shared weight stream): tiles past
+  // the end are processed as all-masked rows
+  const int64_t real_tiles = (p.B + 127) >> 7;
+  const int64_t num_tiles = CLUSTER > 1 ? (real_tiles + gridDim.x - 1) / gridDim.x * gridDim.x : real_tiles;
   const int n_chunks = (p.Np + 127) >> 7;
   const int k_stages = p.Kp / kStageK;
   auto chunk_cols = [&](int c) { return min(128, p.Np - 128 * c); };
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---- weight producer: the whole image once per tile, stage by stage ----------------------------------
     if (ptx::elect_one()) {
       uint32_t it = 0;
@@ -100,36 +111,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
           const uint32_t bytes = static_cast<uint32_t>(chunk_cols(c)) * kStageK * 2;
           for (int ks = 0; ks < k_stages; ++ks, ++it, off += bytes) {
             const int s = it % kStages;
-            if (!ptx::mbar_wait_bounded(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 30); return; }
+            if (!ptx::mbar_wait_bounded(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 30); goto done; }
             ptx::mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-            ptx::bulk_g2s(sbase + s * kStageBytes, p.W + off, bytes, bar_full + 8 * s);
+            if (CLUSTER == 1) {
+              ptx::bulk_g2s(sbase + s * kStageBytes, p.W + off, bytes, bar_full + 8 * s);
+            } else {
+              const uint32_t part = bytes / CLUSTER;      // Nc * 128 B / CLUSTER: a multiple of 16 B for Nc % 16 == 0
+              ptx::bulk_g2s_multicast(sbase + s * kStageBytes + crank * part, p.W + off + crank * part, part, bar_full + 8 * s, kMask);
+            }
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ---- MMA issuer -------------------------------------------------------------------------------------
     if (ptx::elect_one()) {
       uint32_t it = 0, tile_it = 0, chunk_it = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-        if (!ptx::mbar_wait_bounded(bar_aready, tile_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 31); return; }
+        if (!ptx::mbar_wait_bounded(bar_aready, tile_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 31); goto done; }
         ptx::tc_fence_after();
         for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
           const int buf = chunk_it & 1;
           const int nc = chunk_cols(c);
-          if (!ptx::mbar_wait_bounded(bar_dfree + 8 * buf, ((chunk_it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 32); return; }
+          if (!ptx::mbar_wait_bounded(bar_dfree + 8 * buf, ((chunk_it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 32); goto done; }
           ptx::tc_fence_after();
           const uint32_t idesc = ptx::make_idesc_bf16_f32(128, nc);
           for (int ks = 0; ks < k_stages; ++ks, ++it) {
             const int s = it % kStages;
-            if (!ptx::mbar_wait_bounded(bar_full + 8 * s, (it / kStages) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 33); return; }
+            if (!ptx::mbar_wait_bounded(bar_full + 8 * s, (it / kStages) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 33); goto done; }
             ptx::tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kStageK / 16; ++j)
               ptx::umma_f16_ts(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
                                ptx::make_smem_desc(sbase + s * kStageBytes + j * 2 * (nc * 16), nc * 16, 128), idesc,
                                (ks | j) != 0);
-            ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
+            if (CLUSTER == 1) ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
+            else ptx::umma_commit_multicast(bar_empty + 8 * s, kMask);       // ... in every CTA of the cluster
           }
           ptx::umma_commit(bar_dfull + 8 * buf);           // accumulator complete
         }
@@ -137,20 +154,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
     }
   } else {
     // ---- rows: load X into tensor memory, epilogues --------------------------------------------------------
-    const int r = tid;                                     // 0..127
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // two sets of four warps; set s owns accumulator buffer s (so the epilogues of consecutive chunks run side by
+    // side: one warp per scheduler cannot hide the MUFU / tcgen05.ld latencies of a 128-column epilogue) and loads
+    // every second 256-element batch of the rows
+    const int set = warp >> 2;
+    const int r = (warp & 3) * 32 + (tid & 31);            // row of the tile = TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t chunk_it = 0;
+    // rows of a tile: HBM -> registers -> tensor memory, 256 K elements (512 B of the row) per batch, all 32 loads
+    // of a batch in flight before its first tcgen05.st (the st wrapper is a compiler barrier: a load-store-load-store
+    // loop would expose one HBM latency per 64 B)
     auto load_rows = [&](int64_t tile) {
       const int64_t row = tile * 128 + r;
       const uint4* src = reinterpret_cast<const uint4*>(p.X + row * p.Kp);
-      for (int c = 0; c < p.Kp / 32; ++c) {               // 32 bf16 = 16 columns per step
-        uint32_t w[16];
+      for (int b = set; b < p.Kp / 256; b += 2) {
+        uint4 v[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 v = row < p.B ? __ldg(src + 4 * c + q) : make_uint4(0u, 0u, 0u, 0u);
-          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        for (int i = 0; i < 32; ++i) v[i] = row < p.B ? __ldg(src + 32 * b + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { w[4 * q] = v[4 * c + q].x; w[4 * q + 1] = v[4 * c + q].y; w[4 * q + 2] = v[4 * c + q].z; w[4 * q + 3] = v[4 * c + q].w; }
+          ptx::tmem_st16(tmem_base + lane_base + COL_A + 128 * b + 16 * c, w);
         }
-        ptx::tmem_st16(tmem_base + lane_base + COL_A + 16 * c, w);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -216,18 +243,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
     for (; tile < num_tiles; tile += gridDim.x) {
       for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
         const int buf = chunk_it & 1;
+        const bool mine = buf == set, last_chunk = c == n_chunks - 1;
+        if (!mine && !last_chunk) continue;
         if (!ptx::mbar_wait_bounded(bar_dfull + 8 * buf, (chunk_it >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 34); goto done; }
         ptx::tc_fence_after();
         // the last accumulator of the tile is complete => every MMA of the tile has read its A operand: bring the
         // next tile's rows in first, so that its MMAs run under this epilogue
         if (c == n_chunks - 1 && tile + gridDim.x < num_tiles) load_rows(tile + gridDim.x);
-        epilogue(tile, c, buf);
+        if (mine) epilogue(tile, c, buf);
       }
     }
   }
 done:
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();     // nobody leaves while a peer may still multicast into its shared memory
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -270,15 +300,15 @@ bool wide_tc_supported(const MlpModel& m) {
   return true;
 }
 
-// image of layer l: Kp = round_up(K + 1, 64) rows (row K = bias), Np columns (hidden: next layer's Kp, column N is
+// image of layer l: Kp = round_up(K + 1, 256) rows (row K = bias), Np columns (hidden: next layer's Kp, column N is
 // the next layer's bias column: its bias-row entry makes act(.) = 1; last: round_up(N, 16)); chunked by 128 columns,
 // each chunk [Kp/8][Nc][8] bf16 (UMMA canonical K-major, no swizzle)
 int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* const* b_host) {
   for (int l = 0; l < m.n_layers; ++l) {
     const int K = m.dims[l], N = m.dims[l + 1];
-    const int Kp = round_up(K + 1, 64);
+    const int Kp = round_up(K + 1, 256);
     const bool last = l == m.n_layers - 1;
-    const int Np = last ? round_up(N, 16) : round_up(N + 1, 64);
+    const int Np = last ? round_up(N, 16) : round_up(N + 1, 256);
     std::vector<uint16_t> img(static_cast<size_t>(Kp) * Np, 0);
     size_t chunk_off = 0;
     for (int c = 0; c * 128 < Np; ++c) {
@@ -307,7 +337,7 @@ int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* co
 
 size_t wide_tc_scratch_bytes(const MlpModel& m, int64_t rows) {
   int widest = 0;
-  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 64));
+  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 256));
   return 2 * static_cast<size_t>(rows) * widest * 2 + 512;
 }
 
@@ -317,10 +347,10 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
                        int64_t B, void* scratch, float* soft_out, void* hard_out, int hard_bytes) {
   if (B == 0) return NVD_OK;
   int widest = 0;
-  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 64));
+  for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 256));
   __nv_bfloat16* ping = static_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* pong = ping + static_cast<size_t>(B) * widest;
-  const int K0 = m.dims[0], Kp0 = round_up(K0 + 1, 64);
+  const int K0 = m.dims[0], Kp0 = round_up(K0 + 1, 256);
   {
     const int64_t threads = B * (Kp0 / 8);
     const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
@@ -329,10 +359,21 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
     else gather_rows_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(src), src_len, row_stride, K0, Kp0, B, ping);
     NVD_CHECK_LAUNCH();
   }
-  const int smem = kStages * kStageBytes + 256;
-  NVD_CUDA(cudaFuncSetAttribute(mlp_wide_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = kStages * kStageBytes + 16 * kStages + 128;   // stages, full/empty barriers, accumulator / row barriers, TMEM slot
   const int64_t tiles = (B + 127) / 128;
-  const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles));
+  // clusters of 4 (or 2) CTAs share the weight stream when there are enough tiles to fill them
+  int cluster = 1;
+#ifndef NVD_WIDE_CLUSTER
+#define NVD_WIDE_CLUSTER 4
+#endif
+  int want = NVD_WIDE_CLUSTER;
+  if (const char* e = getenv("NVD_WIDE_CLUSTER")) want = atoi(e);     // experiments
+  if (want >= 4 && ctx->sm_count % 4 == 0 && tiles >= ctx->sm_count) cluster = 4;
+  else if (want >= 2 && ctx->sm_count % 2 == 0 && tiles >= ctx->sm_count) cluster = 2;
+  auto kern = cluster == 4 ? mlp_wide_layer_kernel<4> : cluster == 2 ? mlp_wide_layer_kernel<2> : mlp_wide_layer_kernel<1>;
+  NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles));
+  if (cluster > 1) grid = ctx->sm_count;
   for (int l = 0; l < m.n_layers; ++l) {
     WideParams p{};
     const bool last = l == m.n_layers - 1;
@@ -343,14 +384,25 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
     p.hard = last ? hard_out : nullptr;
     p.hard_bytes = hard_bytes;
     p.B = B;
-    p.Kp = round_up(m.dims[l] + 1, 64);
+    p.Kp = round_up(m.dims[l] + 1, 256);
     p.N = m.dims[l + 1];
-    p.Np = last ? round_up(p.N, 16) : round_up(p.N + 1, 64);
+    p.Np = last ? round_up(p.N, 16) : round_up(p.N + 1, 256);
     p.act = m.acts[l];
     p.last = last ? 1 : 0;
     p.abort_flag = ctx->abort_flag;
-    mlp_wide_layer_kernel<<<grid, kThreads, smem, ctx->stream>>>(p);
-    NVD_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NVD_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     std::swap(ping, pong);
   }
   return NVD_OK;
