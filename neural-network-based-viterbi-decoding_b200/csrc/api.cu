@@ -488,7 +488,9 @@ int nvd_mlp_decode_host(nvd_ctx* ctx, int model, const float* y_host, int64_t B,
   for (int64_t r0 = 0; r0 < B; r0 += chunk) {
     const int64_t rows = std::min<int64_t>(chunk, B - r0);
     NVD_CUDA(cudaMemcpyAsync(d_in, y_host + r0 * n_in, static_cast<size_t>(rows) * n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (precision == NVD_PREC_BF16_TC) {
+    if (precision == NVD_PREC_BF16_TC && m->wide) {
+      NVD_TRY(wide_rows(ctx, *m, d_in, NVD_F32, rows * n_in, n_in, rows, d_soft, hard_host ? d_hard : nullptr, 4));
+    } else if (precision == NVD_PREC_BF16_TC) {
       if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
       const int64_t n = rows * n_in;
       f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_in16, n);

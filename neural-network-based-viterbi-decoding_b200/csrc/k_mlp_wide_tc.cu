@@ -364,7 +364,7 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
   // clusters of 4 (or 2) CTAs share the weight stream when there are enough tiles to fill them
   int cluster = 1;
 #ifndef NVD_WIDE_CLUSTER
-#define NVD_WIDE_CLUSTER 4
+#define NVD_WIDE_CLUSTER 2
 #endif
   int want = NVD_WIDE_CLUSTER;
   if (const char* e = getenv("NVD_WIDE_CLUSTER")) want = atoi(e);     // experiments

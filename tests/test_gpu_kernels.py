@@ -216,11 +216,18 @@ def test_mlp_tensor_core_matches_oracle(sim, B):
 
 def test_mlp_tensor_core_unsupported_shape_fails_loudly(sim):
     from nvd import NvdError
+    for dims in ([14, 600, 128], [1036, 30, 2], [14, 64, 256]):     # a layer wider than 511 / more than 128 classes
+        m = _model(dims, [1, 1], seed=3)
+        h = sim.load_mlp(m)
+        assert not sim.mlp_tc_supported(h)
+        with pytest.raises(NvdError):
+            sim.mlp_forward(h, sim.zeros(dims[0] * 2 * 8), "bf16", 8, dims[-1], "bf16")
+    # the fused Monte-Carlo step exists for the reference FNN shape only
     m = _model([14, 64, 128], [1, 1], seed=3)
     h = sim.load_mlp(m)
-    assert not sim.mlp_tc_supported(h)
+    assert sim.mlp_tc_supported(h)                                   # wide-layer path
     with pytest.raises(NvdError):
-        sim.mlp_forward(h, sim.zeros(14 * 2 * 8), "bf16", 8, 128, "bf16")
+        sim.run(h, "133171", 7, [2.0], 1000, 0, mode="fused")
 
 
 # ------------------------------------------------------------------------------------------ K5
