@@ -35,6 +35,11 @@ constexpr int kStageBytes = 128 * kStageK * 2;   // 16 KB (a full 128-column chu
 constexpr int kMaxKp = 512;
 constexpr uint32_t COL_A = 256;          // A operand: columns 256 .. 256 + Kp/2; accumulators: 0..127 and 128..255
 constexpr uint32_t kMaxWaitMs = 4000;
+#ifdef NVD_WIDE_SS
+constexpr int kAOperandBytes = 128 * kMaxKp * 2;   // experiment: A operand [128 x Kp] in shared memory (SS-mode MMAs)
+#else
+constexpr int kAOperandBytes = 0;
+#endif
 
 struct WideParams {
   const __nv_bfloat16* X;   // [B, Kp] rows, 1.0 at column K
@@ -70,7 +75,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
   const uint32_t sbase = ptx::smem_u32(smem);
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-  constexpr int BAR_OFF = kStages * kStageBytes;
+  constexpr int A_OFF = kStages * kStageBytes;
+  constexpr int BAR_OFF = A_OFF + kAOperandBytes;
   const uint32_t bar_full = sbase + BAR_OFF;                 // [kStages]
   const uint32_t bar_empty = sbase + BAR_OFF + 8 * kStages;  // [kStages]
   const uint32_t bar_dfull = sbase + BAR_OFF + 16 * kStages;        // [2]
@@ -142,9 +148,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
             ptx::tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kStageK / 16; ++j)
+#ifdef NVD_WIDE_SS
+              ptx::umma_f16_ss(tmem_base + 128 * buf, ptx::make_smem_desc(sbase + A_OFF + (ks * (kStageK / 16) + j) * 2 * 2048, 2048, 128),
+                               ptx::make_smem_desc(sbase + s * kStageBytes + j * 2 * (nc * 16), nc * 16, 128), idesc,
+                               (ks | j) != 0);
+#else
               ptx::umma_f16_ts(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
                                ptx::make_smem_desc(sbase + s * kStageBytes + j * 2 * (nc * 16), nc * 16, 128), idesc,
                                (ks | j) != 0);
+#endif
             if (CLUSTER == 1) ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
             else ptx::umma_commit_multicast(bar_empty + 8 * s, kMask);       // ... in every CTA of the cluster
           }
@@ -171,6 +183,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
         uint4 v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = row < p.B ? __ldg(src + 32 * b + i) : make_uint4(0u, 0u, 0u, 0u);
+#ifdef NVD_WIDE_SS
+#pragma unroll
+        for (int i = 0; i < 32; ++i)     // canonical K-major layout: 16-byte K chunk kc of row r at kc * 2048 + r * 16
+          *reinterpret_cast<uint4*>(smem + A_OFF + (32 * b + i) * 2048 + r * 16) = v[i];
+#else
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t w[16];
@@ -178,8 +195,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
           for (int q = 0; q < 4; ++q) { w[4 * q] = v[4 * c + q].x; w[4 * q + 1] = v[4 * c + q].y; w[4 * q + 2] = v[4 * c + q].z; w[4 * q + 3] = v[4 * c + q].w; }
           ptx::tmem_st16(tmem_base + lane_base + COL_A + 128 * b + 16 * c, w);
         }
+#endif
       }
+#ifdef NVD_WIDE_SS
+      ptx::fence_proxy_async_smem();
+#else
       ptx::tmem_wait_st();
+#endif
       ptx::tc_fence_before();
       __syncwarp();
       if ((tid & 31) == 0) ptx::mbar_arrive(bar_aready);
@@ -359,7 +381,7 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
     else gather_rows_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(src), src_len, row_stride, K0, Kp0, B, ping);
     NVD_CHECK_LAUNCH();
   }
-  const int smem = kStages * kStageBytes + 16 * kStages + 128;   // stages, full/empty barriers, accumulator / row barriers, TMEM slot
+  const int smem = kStages * kStageBytes + kAOperandBytes + 16 * kStages + 128;   // stages, full/empty barriers, accumulator / row barriers, TMEM slot
   const int64_t tiles = (B + 127) / 128;
   // clusters of 4 (or 2) CTAs share the weight stream when there are enough tiles to fill them
   int cluster = 1;
