@@ -35,11 +35,7 @@ constexpr int kStageBytes = 128 * kStageK * 2;   // 16 KB (a full 128-column chu
 constexpr int kMaxKp = 512;
 constexpr uint32_t COL_A = 256;          // A operand: columns 256 .. 256 + Kp/2; accumulators: 0..127 and 128..255
 constexpr uint32_t kMaxWaitMs = 4000;
-#ifdef NVD_WIDE_SS
-constexpr int kAOperandBytes = 128 * kMaxKp * 2;   // experiment: A operand [128 x Kp] in shared memory (SS-mode MMAs)
-#else
-constexpr int kAOperandBytes = 0;
-#endif
+constexpr int kAOperandBytes = 128 * kMaxKp * 2;   // staging buffer of one tile's rows (tile-canonical layout), 128 KB
 
 struct WideParams {
   const __nv_bfloat16* X;   // [B, Kp] rows, 1.0 at column K
@@ -53,6 +49,7 @@ struct WideParams {
   int act;
   int last;
   int* abort_flag;
+  unsigned long long* debug;   // experiments: issuer wait-time breakdown of CTA 0 (null = off)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -82,12 +79,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
   const uint32_t bar_dfull = sbase + BAR_OFF + 16 * kStages;        // [2]
   const uint32_t bar_dfree = sbase + BAR_OFF + 16 * kStages + 16;   // [2]
   const uint32_t bar_aready = sbase + BAR_OFF + 16 * kStages + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * kStages + 48);
+  const uint32_t bar_xfull = sbase + BAR_OFF + 16 * kStages + 40;    // next tile's rows have landed in the staging buffer
+  const uint32_t bar_xempty = sbase + BAR_OFF + 16 * kStages + 48;   // ... have been moved to tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * kStages + 56);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, CLUSTER); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar_dfull + 8 * b, 1); ptx::mbar_init(bar_dfree + 8 * b, 4); }
     ptx::mbar_init(bar_aready, 8);
+    ptx::mbar_init(bar_xfull, 1);
+    ptx::mbar_init(bar_xempty, 8);
     ptx::mbar_fence_init();
   }
   if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
@@ -110,8 +111,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
   if (warp == 8) {
     // ---- weight producer: the whole image once per tile, stage by stage ----------------------------------
     if (ptx::elect_one()) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t it = 0, xt = 0;
+      const uint32_t x_bytes = 128u * static_cast<uint32_t>(p.Kp) * 2u;
+      auto stage_rows = [&](int64_t t) {     // tile-canonical activations: one contiguous block per tile
+        if (t >= real_tiles) { ptx::mbar_arrive(bar_xfull); return; }     // cluster padding tile: nothing to fetch
+        ptx::mbar_arrive_expect_tx(bar_xfull, x_bytes);
+        for (uint32_t o = 0; o < x_bytes; o += 32768)
+          ptx::bulk_g2s(sbase + A_OFF + o, reinterpret_cast<const uint8_t*>(p.X) + static_cast<size_t>(t) * x_bytes + o, 32768, bar_xfull);
+      };
+      if (static_cast<int64_t>(blockIdx.x) < num_tiles) stage_rows(blockIdx.x);
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++xt) {
+        // the staging buffer is free once the row warps have moved this tile into tensor memory: fetch the next
+        // tile's rows now, a whole tile of MMAs ahead of their use
+        if (tile + gridDim.x < num_tiles) {
+          if (!ptx::mbar_wait_bounded(bar_xempty, xt & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 35); goto done; }
+          stage_rows(tile + gridDim.x);
+        }
         size_t off = 0;
         for (int c = 0; c < n_chunks; ++c) {
           const uint32_t bytes = static_cast<uint32_t>(chunk_cols(c)) * kStageK * 2;
@@ -133,18 +148,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
     // ---- MMA issuer -------------------------------------------------------------------------------------
     if (ptx::elect_one()) {
       uint32_t it = 0, tile_it = 0, chunk_it = 0;
+      long long t_a = 0, t_d = 0, t_f = 0, t_i = 0, t0 = clock64(), tt;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        tt = clock64();
         if (!ptx::mbar_wait_bounded(bar_aready, tile_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 31); goto done; }
+        t_a += clock64() - tt;
         ptx::tc_fence_after();
         for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
           const int buf = chunk_it & 1;
           const int nc = chunk_cols(c);
+          tt = clock64();
           if (!ptx::mbar_wait_bounded(bar_dfree + 8 * buf, ((chunk_it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 32); goto done; }
+          t_d += clock64() - tt;
           ptx::tc_fence_after();
           const uint32_t idesc = ptx::make_idesc_bf16_f32(128, nc);
           for (int ks = 0; ks < k_stages; ++ks, ++it) {
             const int s = it % kStages;
+            tt = clock64();
             if (!ptx::mbar_wait_bounded(bar_full + 8 * s, (it / kStages) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 33); goto done; }
+            t_f += clock64() - tt;
+            tt = clock64();
             ptx::tc_fence_after();
 #pragma unroll
             for (int j = 0; j < kStageK / 16; ++j)
@@ -159,9 +182,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
 #endif
             if (CLUSTER == 1) ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
             else ptx::umma_commit_multicast(bar_empty + 8 * s, kMask);       // ... in every CTA of the cluster
+            t_i += clock64() - tt;
           }
           ptx::umma_commit(bar_dfull + 8 * buf);           // accumulator complete
         }
+      }
+      if (p.debug != nullptr && blockIdx.x == 0) {
+        p.debug[0] = clock64() - t0; p.debug[1] = t_a; p.debug[2] = t_d; p.debug[3] = t_f; p.debug[4] = t_i; p.debug[5] = tile_it;
       }
     }
   } else {
@@ -173,50 +200,49 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
     const int r = (warp & 3) * 32 + (tid & 31);            // row of the tile = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t chunk_it = 0;
-    // rows of a tile: HBM -> registers -> tensor memory, 256 K elements (512 B of the row) per batch, all 32 loads
-    // of a batch in flight before its first tcgen05.st (the st wrapper is a compiler barrier: a load-store-load-store
-    // loop would expose one HBM latency per 64 B)
-    auto load_rows = [&](int64_t tile) {
-      const int64_t row = tile * 128 + r;
-      const uint4* src = reinterpret_cast<const uint4*>(p.X + row * p.Kp);
+    // rows of a tile: staging buffer (filled by the producer's bulk copy a tile ahead) -> registers -> tensor memory.
+    // Tile-canonical layout: the 16-byte K chunk kc of row r sits at kc * 2048 + r * 16, so a warp reads 512
+    // contiguous bytes per request (no bank conflicts) and the SS-mode experiment can use the buffer as it is.
+    uint32_t rows_it = 0;
+    auto load_rows = [&](int64_t) {
+      if (!ptx::mbar_wait_bounded(bar_xfull, rows_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 36); return; }
+      ++rows_it;
+#ifndef NVD_WIDE_SS
       for (int b = set; b < p.Kp / 256; b += 2) {
-        uint4 v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = row < p.B ? __ldg(src + 32 * b + i) : make_uint4(0u, 0u, 0u, 0u);
-#ifdef NVD_WIDE_SS
-#pragma unroll
-        for (int i = 0; i < 32; ++i)     // canonical K-major layout: 16-byte K chunk kc of row r at kc * 2048 + r * 16
-          *reinterpret_cast<uint4*>(smem + A_OFF + (32 * b + i) * 2048 + r * 16) = v[i];
-#else
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t w[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { w[4 * q] = v[4 * c + q].x; w[4 * q + 1] = v[4 * c + q].y; w[4 * q + 2] = v[4 * c + q].z; w[4 * q + 3] = v[4 * c + q].w; }
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(smem + A_OFF + (32 * b + 4 * c + q) * 2048 + r * 16);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+          }
           ptx::tmem_st16(tmem_base + lane_base + COL_A + 128 * b + 16 * c, w);
         }
-#endif
       }
-#ifdef NVD_WIDE_SS
-      ptx::fence_proxy_async_smem();
-#else
       ptx::tmem_wait_st();
 #endif
       ptx::tc_fence_before();
       __syncwarp();
-      if ((tid & 31) == 0) ptx::mbar_arrive(bar_aready);
+      if ((tid & 31) == 0) {
+#ifndef NVD_WIDE_SS
+        ptx::mbar_arrive(bar_xempty);     // SS mode: the MMAs read the staging buffer; it is released with the tile
+#endif
+        ptx::mbar_arrive(bar_aready);
+      }
     };
     auto epilogue = [&](int64_t tile, int c, int buf) {
       const int64_t row = tile * 128 + r;
       const int nc = chunk_cols(c);
       const uint32_t d = tmem_base + lane_base + 128 * buf;
       if (!p.last) {
-        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.Y) + row * p.Np + 128 * c;
+        // next layer's rows in the same tile-canonical layout: 16 B per (row, 8 columns), 512 contiguous bytes per warp
+        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.Y) + (static_cast<size_t>(tile) * (p.Np / 8) + 16 * c) * 1024 + r * 8;
         for (int c0 = 0; c0 < nc; c0 += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(d + c0, v);
           ptx::tmem_wait_ld();
-          if (row < p.B) {
+          if (tile < real_tiles) {     // pad rows of the last tile are written too (the buffers hold whole tiles)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (c0 + 8 * q < nc) {
@@ -225,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
                 o.y = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 2]), p.act), apply_act(__uint_as_float(v[8 * q + 3]), p.act));
                 o.z = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 4]), p.act), apply_act(__uint_as_float(v[8 * q + 5]), p.act));
                 o.w = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 6]), p.act), apply_act(__uint_as_float(v[8 * q + 7]), p.act));
-                *reinterpret_cast<uint4*>(out + c0 + 8 * q) = o;
+                *reinterpret_cast<uint4*>(out + ((c0 >> 3) + q) * 1024) = o;
               }
             }
           }
@@ -271,6 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
         ptx::tc_fence_after();
         // the last accumulator of the tile is complete => every MMA of the tile has read its A operand: bring the
         // next tile's rows in first, so that its MMAs run under this epilogue
+#ifdef NVD_WIDE_SS
+        if (c == n_chunks - 1) { __syncwarp(); if ((tid & 31) == 0) ptx::mbar_arrive(bar_xempty); }
+#endif
         if (c == n_chunks - 1 && tile + gridDim.x < num_tiles) load_rows(tile + gridDim.x);
         if (mine) epilogue(tile, c, buf);
       }
@@ -291,18 +320,20 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, int64_t src_len, i
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // one thread = 8 output columns
   const int per_row = Kp / 8;
   const int64_t row = i / per_row;
-  if (row >= B) return;
+  if (row >= ((B + 127) & ~int64_t(127))) return;      // whole tiles: the pad rows of the last tile are zero-filled
   const int c0 = static_cast<int>(i - row * per_row) * 8;
   __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = c0 + j;
     float f = 0.0f;
-    if (col < K) { const int64_t s = row * row_stride + col; f = s < src_len ? static_cast<float>(src[s]) : 0.0f; }
+    if (row >= B) f = 0.0f;
+    else if (col < K) { const int64_t s = row * row_stride + col; f = s < src_len ? static_cast<float>(src[s]) : 0.0f; }
     else if (col == K) f = 1.0f;
     v[j] = __float2bfloat16_rn(f);
   }
-  *reinterpret_cast<uint4*>(X + row * Kp + c0) = *reinterpret_cast<const uint4*>(v);
+  // tile-canonical: [tile][Kp / 8][128 rows][8]
+  *reinterpret_cast<uint4*>(X + ((row >> 7) * (Kp / 8) + (c0 >> 3)) * 1024 + (row & 127) * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
 uint16_t bf16_rn(float f) {
@@ -360,7 +391,7 @@ int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* co
 size_t wide_tc_scratch_bytes(const MlpModel& m, int64_t rows) {
   int widest = 0;
   for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 256));
-  return 2 * static_cast<size_t>(rows) * widest * 2 + 512;
+  return 2 * static_cast<size_t>((rows + 127) & ~int64_t(127)) * widest * 2 + 512;
 }
 
 // rows: `B` rows taken from `src` (dtype NVD_F32 / NVD_BF16 / NVD_I32_TRUNC) at element stride `row_stride`
@@ -371,17 +402,17 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
   int widest = 0;
   for (int l = 0; l < m.n_layers; ++l) widest = std::max(widest, round_up(m.dims[l] + 1, 256));
   __nv_bfloat16* ping = static_cast<__nv_bfloat16*>(scratch);
-  __nv_bfloat16* pong = ping + static_cast<size_t>(B) * widest;
+  __nv_bfloat16* pong = ping + static_cast<size_t>((B + 127) & ~int64_t(127)) * widest;
   const int K0 = m.dims[0], Kp0 = round_up(K0 + 1, 256);
   {
-    const int64_t threads = B * (Kp0 / 8);
+    const int64_t threads = ((B + 127) & ~int64_t(127)) * (Kp0 / 8);
     const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
     if (src_dtype == NVD_F32) gather_rows_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(src), src_len, row_stride, K0, Kp0, B, ping);
     else if (src_dtype == NVD_BF16) gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(src), src_len, row_stride, K0, Kp0, B, ping);
     else gather_rows_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(src), src_len, row_stride, K0, Kp0, B, ping);
     NVD_CHECK_LAUNCH();
   }
-  const int smem = kStages * kStageBytes + kAOperandBytes + 16 * kStages + 128;   // stages, full/empty barriers, accumulator / row barriers, TMEM slot
+  const int smem = kStages * kStageBytes + kAOperandBytes + 16 * kStages + 128;   // 229 856 B   // stages, full/empty barriers, accumulator / row barriers, TMEM slot
   const int64_t tiles = (B + 127) / 128;
   // clusters of 4 (or 2) CTAs share the weight stream when there are enough tiles to fill them
   int cluster = 1;
@@ -412,6 +443,11 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
     p.act = m.acts[l];
     p.last = last ? 1 : 0;
     p.abort_flag = ctx->abort_flag;
+    static unsigned long long* dbg = nullptr;
+    if (getenv("NVD_WIDE_DEBUG")) {
+      if (!dbg) cudaMalloc(&dbg, 64);
+      p.debug = dbg;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -425,6 +461,13 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NVD_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    if (p.debug) {
+      unsigned long long h[6];
+      cudaMemcpyAsync(h, dbg, 48, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "wide layer %d: rows %lld  issuer clk total %llu  wait a_ready %llu  wait d_free %llu  wait full %llu  issue %llu  tiles %llu\n",
+              l, static_cast<long long>(B), h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
     std::swap(ping, pong);
   }
   return NVD_OK;
