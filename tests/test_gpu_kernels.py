@@ -387,3 +387,37 @@ def test_window_decode_matches_dense_rows(sim, precision):
     from nvd import NvdError
     with pytest.raises(NvdError):
         sim.window_decode(h, d_stream, "f32", n_sym, 2, n_win + 1, 2, precision)   # runs past the end of the stream
+
+
+@pytest.mark.parametrize("H,B,T_enc,T_dec", [(20, 1, 200, 200), (20, 131, 70, 45), (16, 700, 33, 64)])
+def test_lstm_tensor_core_ragged_shapes(sim, H, B, T_enc, T_dec):
+    """Edge cases of the tcgen05 recurrence: a single frame, T_enc != T_dec, lengths that are not multiples of the
+    32-step staging window; against the fp32 kernel (teacher-forced logits) and its own packed decisions."""
+    from nvd import weights
+    p = olstm.init_params(H, seed=7)
+    rng = np.random.default_rng(B + T_enc)
+    p["enc_b"] = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    p["dec_b"] = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    y = rng.standard_normal((B, T_enc)).astype(np.float32)
+    dec_in = np.sign(rng.standard_normal((B, T_dec))).astype(np.float32)
+    h = sim.load_lstm(weights.LstmModel(**p))
+    d_y, d_dec = sim.to_device(y), sim.to_device(dec_in)
+    nb = (T_dec + 7) // 8
+    tc_l, tc_h = sim.lstm_forward(h, d_y, "f32", d_dec, T_enc, T_dec, B, fast_math=2)
+    ref_l, _ = sim.lstm_forward(h, d_y, "f32", d_dec, T_enc, T_dec, B, fast_math=False)
+    got, ref = tc_l.download(np.float32, (B, T_dec)), ref_l.download(np.float32, (B, T_dec))
+    assert np.abs(got - ref).max() <= 3e-2
+    want = olstm.seq2seq_forward(y, dec_in, p, dtype=np.float64)
+    assert np.abs(got - want).max() <= 3e-2
+    hard = np.unpackbits(tc_h.download(np.uint8, (B, nb)), axis=1, bitorder="little")[:, :T_dec]
+    assert (hard == (got > 0)).all()
+
+
+def test_mlp_wide_single_row_and_empty(sim):
+    m = _model([200, 500, 2], [1, 1], seed=9, bias=0.1)
+    h = sim.load_mlp(m)
+    y = np.random.default_rng(1).standard_normal((1, 200)).astype(np.float32)
+    soft_b, hard_b = sim.mlp_forward(h, sim.to_device(y), "f32", 1, 2, "bf16", want_soft=True, hard_bytes=4)
+    want = omlp.forward(y, m.Ws, m.bs, m.acts, dtype=np.float64)
+    assert np.abs(soft_b.download(np.float32, (1, 2)) - want).max() <= 2e-2
+    sim.mlp_forward(h, sim.to_device(y), "f32", 0, 2, "bf16", want_soft=False, hard_bytes=4)      # B = 0 is a no-op
