@@ -29,13 +29,21 @@ namespace nvd {
 namespace {
 
 constexpr int kThreads = 320;            // warps 0-7: rows / epilogues (two sets of four), warp 8: weight producer, warp 9: MMA issuer
-constexpr int kStages = 6;              // 96 KB of weights in flight (13 stages measured no faster: not the bound)
+#ifdef NVD_WIDE_DIRECT_ROWS
+constexpr int kStages = 13;             // experiment: no row staging buffer, 208 KB of weights in flight instead
+#else
+constexpr int kStages = 6;              // 96 KB of weights in flight next to the 128 KB row staging buffer
+#endif
 constexpr int kStageK = 64;              // k extent of one stage
 constexpr int kStageBytes = 128 * kStageK * 2;   // 16 KB (a full 128-column chunk)
 constexpr int kMaxKp = 512;
 constexpr uint32_t COL_A = 256;          // A operand: columns 256 .. 256 + Kp/2; accumulators: 0..127 and 128..255
 constexpr uint32_t kMaxWaitMs = 4000;
+#ifdef NVD_WIDE_DIRECT_ROWS
+constexpr int kAOperandBytes = 0;
+#else
 constexpr int kAOperandBytes = 128 * kMaxKp * 2;   // staging buffer of one tile's rows (tile-canonical layout), 128 KB
+#endif
 
 struct WideParams {
   const __nv_bfloat16* X;   // [B, Kp] rows, 1.0 at column K
@@ -114,6 +122,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
       uint32_t it = 0, xt = 0;
       const uint32_t x_bytes = 128u * static_cast<uint32_t>(p.Kp) * 2u;
       auto stage_rows = [&](int64_t t) {     // tile-canonical activations: one contiguous block per tile
+#ifdef NVD_WIDE_DIRECT_ROWS
+        if (t < real_tiles)
+          for (uint32_t o = 0; o < x_bytes; o += 16384)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(p.X) + static_cast<size_t>(t) * x_bytes + o), "r"(16384u) : "memory");
+        return;
+#endif
         if (t >= real_tiles) { ptx::mbar_arrive(bar_xfull); return; }     // cluster padding tile: nothing to fetch
         ptx::mbar_arrive_expect_tx(bar_xfull, x_bytes);
         for (uint32_t o = 0; o < x_bytes; o += 32768)
@@ -124,7 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
         // the staging buffer is free once the row warps have moved this tile into tensor memory: fetch the next
         // tile's rows now, a whole tile of MMAs ahead of their use
         if (tile + gridDim.x < num_tiles) {
+#ifndef NVD_WIDE_DIRECT_ROWS
           if (!ptx::mbar_wait_bounded(bar_xempty, xt & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 35); goto done; }
+#endif
           stage_rows(tile + gridDim.x);
         }
         size_t off = 0;
@@ -204,7 +220,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
     // Tile-canonical layout: the 16-byte K chunk kc of row r sits at kc * 2048 + r * 16, so a warp reads 512
     // contiguous bytes per request (no bank conflicts) and the SS-mode experiment can use the buffer as it is.
     uint32_t rows_it = 0;
-    auto load_rows = [&](int64_t) {
+    auto load_rows = [&](int64_t tile_to_load) {
+#ifdef NVD_WIDE_DIRECT_ROWS
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.X) + static_cast<size_t>(tile_to_load) * (p.Kp / 8) * 128 + r;
+        const bool have = tile_to_load < real_tiles;
+        for (int b = set; b < p.Kp / 256; b += 2) {
+          uint4 v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = have ? __ldg(src + (32 * b + i) * 128) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { w[4 * q] = v[4 * c + q].x; w[4 * q + 1] = v[4 * c + q].y; w[4 * q + 2] = v[4 * c + q].z; w[4 * q + 3] = v[4 * c + q].w; }
+            ptx::tmem_st16(tmem_base + lane_base + COL_A + 128 * b + 16 * c, w);
+          }
+        }
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) ptx::mbar_arrive(bar_aready);
+        return;
+      }
+#endif
       if (!ptx::mbar_wait_bounded(bar_xfull, rows_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 36); return; }
       ++rows_it;
 #ifndef NVD_WIDE_SS
