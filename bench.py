@@ -270,6 +270,34 @@ def main():
             ms_l = sim.elapsed_ms(e0, e1) / reps
             other[name] = {"ms": ms_l, "gbit_per_s": Bl * Ll / (ms_l * 1e-3) / 1e9, "mframes_per_s": Bl / (ms_l * 1e-3) / 1e6}
 
+    # ---------------- sliding-window decoder (fnn_viterbi_seq_predict, 200-500x4-2) on the wide-layer tcgen05 kernel ---
+    seq = None
+    if not args.no_staged and world == 1:
+        from nvd import weights as _w2, _lib as _l2
+        dims_s = [200, 500, 500, 500, 500, 2]
+        rng = np.random.default_rng(3)
+        Ws_s = [(rng.standard_normal((a, b)) * np.sqrt(2.0 / a)).astype(np.float32) for a, b in zip(dims_s[:-1], dims_s[1:])]
+        bs_s = [np.zeros(b, np.float32) for b in dims_s[1:]]
+        hs = sim.load_mlp(_w2.MlpModel(Ws_s, bs_s, [1] * 5))
+        n_win = 1 << 19
+        n_sym = 2 * (n_win - 1) + 200
+        d_stream = sim.to_device(rng.standard_normal(n_sym).astype(np.float32))
+        d_bits = sim.alloc(n_win)
+        def seq_step():
+            _l2.check(sim.lib.nvd_window_decode(sim.ctx, hs, d_stream.ptr, _l2.DTYPES["f32"], n_sym, 2, n_win,
+                                                _l2.PRECISIONS["bf16"], None, d_bits.ptr, 1))
+        seq_step(); sim.sync()
+        e0, e1 = sim.event(), sim.event()
+        sim.record(e0)
+        for _ in range(3):
+            seq_step()
+        sim.record(e1); sim.sync()
+        ms_s = sim.elapsed_ms(e0, e1) / 3
+        mac = sum(a * b for a, b in zip(dims_s[:-1], dims_s[1:]))
+        seq = {"workload": "fnn_viterbi_seq_predict: 200-500x4-2 tanh MLP over stride-2 windows, nvd_window_decode bf16", "windows": n_win,
+               "ms": ms_s, "mbit_per_s": n_win / (ms_s * 1e-3) / 1e6, "tflops": 2 * mac * n_win / (ms_s * 1e-3) / 1e12,
+               "frac_of_bf16_peak": 2 * mac * n_win / (ms_s * 1e-3) / 1e12 / peaks["bf16_burst"]}
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
@@ -316,6 +344,7 @@ def main():
         "allreduce_ms": ar_ms,
         "staged": staged,
         "rnn_viterbi": other,
+        "seq_predict": seq,
         "e2e_counters": [int(x) for x in c_e2e],
     }
     print(json.dumps(line), flush=True)
