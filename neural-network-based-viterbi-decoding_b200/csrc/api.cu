@@ -696,7 +696,8 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
   const uint64_t frames = cfg->frames;
   // 128 frames per tile, 4 tile streams per SM: slices of a whole number of waves keep the tails small.  The first
   // copy-in and the last copy-out are the only transfers nothing overlaps, so the schedule starts and ends with
-  // short slices (4, 8 waves) around 24-wave ones.
+  // short slices (4, 8 waves) around 24-wave ones (96-wave slices measured slower: the copy-out of a long slice is
+  // exposed behind the short kernels that follow it).
   const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * 4 * 128;
   std::vector<uint64_t> slices;
   {
