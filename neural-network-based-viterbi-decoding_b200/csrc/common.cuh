@@ -98,6 +98,9 @@ struct nvd_ctx {
   // host-buffer fused pipeline: copy-in / copy-out streams and per-slice events (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> slice_ev;
+  uint32_t* slice_flags = nullptr;       // device: one word per input slice of the streaming host step
+  uint32_t* slice_ones = nullptr;        // pinned: the value copied into a flag
+  static constexpr int kMaxSlices = 1024;
   // staged-pipeline stage timing
   cudaEvent_t stage_ev[6] = {nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -145,6 +148,6 @@ int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y
 // pred (one byte per frame, may be null) instead of being a function of the frame index
 int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float sigma, int snr_idx,
                         uint64_t frame0, uint64_t frames, uint64_t* counters, const uint8_t* info = nullptr,
-                        uint8_t* pred = nullptr);
+                        uint8_t* pred = nullptr, const uint32_t* slice_flags = nullptr, int64_t slice_frames = 0);
 
 }  // namespace nvd

@@ -1,6 +1,8 @@
 """GPU tests of the whole Monte-Carlo step (encode -> channel -> decode -> count) through the C ABI:
 fused == staged, shard invariance, oracle parity of the counters, host-buffer (end-to-end) form,
 and size-independent properties at BASELINE.json's full size (2^24 frames / SNR point)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -96,6 +98,24 @@ def test_host_buffer_fused_step_equals_staged_step(sim, handle, frames):
     assert [be, fe] == [int(c_f[0]), int(c_f[1])]
     c_nopred = sim.run_host(handle, "133171", 7, 1.0, info, None, frame0=777, snr_idx=3, mode="fused")
     assert (c_nopred == c_f).all()
+    # pinned buffers take the streaming form: one launch, info words arriving while the kernel runs (flagged slices),
+    # decisions stored straight into the mapped host buffer; repeated to catch stale flags / cached info bytes
+    info_p, pred_p = sim.pinned(frames), sim.pinned(frames)
+    os.environ["NVD_HOST_STEP"] = "streaming"        # (default: streaming only when no decisions are requested)
+    for rep in range(3):
+        info_r = np.roll(info, rep)
+        info_p[:] = info_r
+        pred_p[:] = 253
+        c_p = sim.run_host(handle, "133171", 7, 1.0, info_p, pred_p, frame0=777, snr_idx=3, mode="fused")
+        if rep == 0:
+            assert (c_p == c_s).all() and (pred_p == pred_s).all()
+        else:
+            pred_r = np.full(frames, 252, np.uint8)
+            c_r = sim.run_host(handle, "133171", 7, 1.0, info_r, pred_r, frame0=777, snr_idx=3, mode="staged")
+            assert (c_p == c_r).all() and (pred_p == pred_r).all()
+    os.environ.pop("NVD_HOST_STEP")
+    c_p2 = sim.run_host(handle, "133171", 7, 1.0, info_p, None, frame0=777, snr_idx=3, mode="fused")
+    assert (c_p2 == c_p).all()
 
 
 def test_full_size_properties(sim, handle):
