@@ -19,6 +19,22 @@ namespace nvd {
 // K0: info words.  L <= 16: frame f carries class (f mod 2^L), stored time-packed.
 //     L  > 16: Philox stream kStreamInfo, 128 bits per block.
 // ---------------------------------------------------------------------------------------------
+// L <= 8, 16 frames (one 16-byte store) per thread
+__global__ void __launch_bounds__(256) source_small16_kernel(int L, uint64_t frame0, int64_t n16, uint4* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n16) return;
+  const uint32_t mask = (1u << L) - 1u;
+  const uint32_t base = static_cast<uint32_t>(frame0 + 16 * static_cast<uint64_t>(i));
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    w[q] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[q] |= bitrev_L((base + 4 * q + k) & mask, L) << (8 * k);
+  }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(256) source_small_kernel(int L, uint64_t frame0, int64_t B,
                                                            uint8_t* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;  // 4 frames each
@@ -69,7 +85,14 @@ __global__ void __launch_bounds__(256) source_philox_kernel(uint64_t seed, int L
 
 int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info) {
   if (B == 0) return NVD_OK;
-  if (L <= 16) {
+  if (L <= 8 && reinterpret_cast<uintptr_t>(info) % 16 == 0 && B >= 16) {
+    const int64_t n16 = B / 16;
+    source_small16_kernel<<<static_cast<unsigned>((n16 + 255) / 256), 256, 0, ctx->stream>>>(L, frame0, n16, reinterpret_cast<uint4*>(info));
+    NVD_CHECK_LAUNCH();
+    const int64_t rest = B - 16 * n16;     // tail frames: the scalar kernel, 4-byte aligned start
+    if (rest > 0)
+      source_small_kernel<<<static_cast<unsigned>(((rest + 3) / 4 + 255) / 256), 256, 0, ctx->stream>>>(L, frame0 + 16 * n16, rest, info + 16 * n16);
+  } else if (L <= 16) {
     const int64_t threads = (B + 3) / 4;
     source_small_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(
         L, frame0, B, info);
@@ -122,6 +145,32 @@ __global__ void __launch_bounds__(256) encode_vec16_kernel(int code, int L, int 
   out[2 * i + 1] = make_uint4(wo[4], wo[5], wo[6], wo[7]);
 }
 
+// K1 table path, frames of one byte (L <= 8): the code word is a function of the info byte alone (zero start state), so
+// each block builds the 256-entry table with the same encode16 once and every thread translates 16 bytes with 16
+// shared-memory lookups — the shift-XOR path spends ~25 instructions per byte and is instruction-bound, not HBM-bound.
+__global__ void __launch_bounds__(256) encode_lut16_kernel(int code, int L, int64_t n16, const uint4* __restrict__ in,
+                                                           uint4* __restrict__ out) {
+  __shared__ uint16_t lut[256];
+  {
+    const uint32_t u = threadIdx.x & ((L < 8) ? ((1u << L) - 1u) : 0xFFu);
+    lut[threadIdx.x] = static_cast<uint16_t>(encode16(u, 0u, code, true, L));
+  }
+  __syncthreads();
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 w = __ldg(in + i);
+  const uint32_t wi[4] = {w.x, w.y, w.z, w.w};
+  uint32_t wo[8];
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t a = lut[(wi[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+    const uint32_t b = lut[(wi[k >> 2] >> (8 * ((k & 3) + 1))) & 0xFFu];
+    wo[k >> 1] = a | (b << 16);
+  }
+  out[2 * i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  out[2 * i + 1] = make_uint4(wo[4], wo[5], wo[6], wo[7]);
+}
+
 // K1 byte path: any L; one input byte per thread over [g_begin, g_end).
 __global__ void __launch_bounds__(256) encode_bytes_kernel(int code, int L, int S_in, int S_out,
                                                            int64_t g_begin, int64_t g_end,
@@ -152,8 +201,8 @@ int launch_encode(nvd_ctx* ctx, int code, const uint8_t* info, int L, int64_t B,
     const int64_t n16 = total / 16;
     const unsigned grid = static_cast<unsigned>((n16 + 255) / 256);
     if (S_in == 1)
-      encode_vec16_kernel<1><<<grid, 256, 0, ctx->stream>>>(
-          code, L, S_in, n16, reinterpret_cast<const uint4*>(info), reinterpret_cast<uint4*>(coded));
+      encode_lut16_kernel<<<grid, 256, 0, ctx->stream>>>(code, L, n16, reinterpret_cast<const uint4*>(info),
+                                                         reinterpret_cast<uint4*>(coded));
     else
       encode_vec16_kernel<0><<<grid, 256, 0, ctx->stream>>>(
           code, L, S_in, n16, reinterpret_cast<const uint4*>(info), reinterpret_cast<uint4*>(coded));
