@@ -75,11 +75,14 @@ __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const
 // two noise8 calls as the fused pipeline's producer warps — 4 Philox blocks and 7-8 Box-Muller pairs per thread
 // with no per-block index arithmetic (2.3x fewer instructions per frame than the block-per-thread kernel).
 // A warp's 32 rows are contiguous in y, so its 4- / 8-byte stores fill whole sectors between them.
-template <int kDtype>
+// kN: compile-time symbol count (14 for the reference L = 7: the unused Box-Muller pair and every bound check
+// disappear), 0 = run-time n
+template <int kDtype, int kN>
 __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk, const uint8_t* __restrict__ coded,
-                                                            int n, int64_t B, float sigma, uint32_t stream_word,
+                                                            int n_rt, int64_t B, float sigma, uint32_t stream_word,
                                                             uint64_t frame0, typename OutT<kDtype>::type* __restrict__ y) {
   using T = typename OutT<kDtype>::type;
+  const int n = kN ? kN : n_rt;
   // a warp's 32 rows go through a shared staging block so that they leave as full 16-byte vectors: per-thread
   // 4-byte stores at a 28-byte stride cost seven partial-sector writes per sector in L2
   __shared__ __align__(16) T stage[8][32 * 16];
@@ -128,10 +131,15 @@ int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float s
   const PhiloxKeys rk = make_philox_keys(ctx->seed);
   if (n <= 16 && (n & 1) == 0) {
     const unsigned fgrid = static_cast<unsigned>((B + 255) / 256);
+#define NVD_LAUNCH_FRAME(DT, CT)                                                                                          \
+  do {                                                                                                                    \
+    if (n == 14) channel_frame_kernel<DT, 14><<<fgrid, 256, 0, ctx->stream>>>(rk, coded, n, B, sigma, sw, frame0, static_cast<CT*>(y)); \
+    else channel_frame_kernel<DT, 0><<<fgrid, 256, 0, ctx->stream>>>(rk, coded, n, B, sigma, sw, frame0, static_cast<CT*>(y));         \
+  } while (0)
     switch (out_dtype) {
-      case NVD_F32: channel_frame_kernel<NVD_F32><<<fgrid, 256, 0, ctx->stream>>>(rk, coded, n, B, sigma, sw, frame0, static_cast<float*>(y)); break;
-      case NVD_BF16: channel_frame_kernel<NVD_BF16><<<fgrid, 256, 0, ctx->stream>>>(rk, coded, n, B, sigma, sw, frame0, static_cast<__nv_bfloat16*>(y)); break;
-      case NVD_I32_TRUNC: channel_frame_kernel<NVD_I32_TRUNC><<<fgrid, 256, 0, ctx->stream>>>(rk, coded, n, B, sigma, sw, frame0, static_cast<int32_t*>(y)); break;
+      case NVD_F32: NVD_LAUNCH_FRAME(NVD_F32, float); break;
+      case NVD_BF16: NVD_LAUNCH_FRAME(NVD_BF16, __nv_bfloat16); break;
+      case NVD_I32_TRUNC: NVD_LAUNCH_FRAME(NVD_I32_TRUNC, int32_t); break;
       default:
         set_error("nvd_channel: unknown out_dtype %d", out_dtype);
         return NVD_ERR_INVALID;
