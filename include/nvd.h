@@ -6,7 +6,7 @@
  * behind module-level functions that exchange numpy arrays and whose heavy lifting is done by
  * Python loops and a TensorFlow-1.x session.  Each entry point below names the reference
  * function (file:line under /root/reference) whose work it replaces; the Python drop-in
- * modules (neural-network-based-viterbi-decoding_b200/src/*.py) bind them through ctypes, and
+ * modules (the .py files under neural-network-based-viterbi-decoding_b200/src) bind them through ctypes, and
  * INTEGRATION.md shows the stub a maintainer of the reference would add.
  *
  * Conventions
