@@ -720,13 +720,15 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
   NVD_CUDA(cudaMemsetAsync(ctx->slice_flags, 0, n_slices * sizeof(uint32_t), ctx->stream));
   NVD_CUDA(cudaEventRecord(ctx->slice_ev[0], ctx->stream));          // flags cleared (and earlier work done) before
   NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->slice_ev[0], 0));  // the first slice may land
-  NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, frames,
-                              ctx->counters_scratch, d_info, pred_dev_visible, ctx->slice_flags, static_cast<int64_t>(slice)));
+  // the copies are queued BEFORE the kernel that waits for them: a tool that makes launches synchronous (ncu) must
+  // not be able to park the host inside the launch with the copies still unissued
   for (size_t s = 0; s < n_slices; ++s) {
     const uint64_t off = s * slice, n = std::min<uint64_t>(slice, frames - off);
     NVD_CUDA(cudaMemcpyAsync(d_info + off, info_host + off, n, cudaMemcpyHostToDevice, ctx->copy_in));
     NVD_CUDA(cudaMemcpyAsync(ctx->slice_flags + s, ctx->slice_ones, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in));
   }
+  NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, frames,
+                              ctx->counters_scratch, d_info, pred_dev_visible, ctx->slice_flags, static_cast<int64_t>(slice)));
   NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
   NVD_TRY(nvd_sync(ctx));
@@ -752,10 +754,12 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
     }
     cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on some drivers
     // measured (2^24 frames, 1 B200): counters only 1.185 ms streaming vs 1.205 ms sliced; with decisions 1.365 ms
-    // streaming (1-byte stores into mapped host memory are slow over PCIe) vs 1.229 ms sliced -> streaming is the
-    // default only when no decisions are asked for (NVD_HOST_STEP=streaming / sliced overrides)
+    // streaming (1-byte stores into mapped host memory are slow over PCIe) vs 1.229 ms sliced.  The sliced form is
+    // the default: a 1.7 % gain does not pay for a kernel that waits on copies issued beside it (a profiler that
+    // replays the kernel restores the flags but not the copies; the bounded wait then aborts the launch).
+    // NVD_HOST_STEP=streaming opts in.
     const char* force = getenv("NVD_HOST_STEP");
-    const bool want = force ? (strcmp(force, "streaming") == 0) : (pred_host == nullptr);
+    const bool want = force && strcmp(force, "streaming") == 0;
     if (want && info_pinned && pred_ok && cfg->frames > 0)
       return mc_run_host_streaming(ctx, cfg, m, snr_db, snr_idx, info_host, pred_dev, counters_host);
   }

@@ -101,7 +101,7 @@ def test_host_buffer_fused_step_equals_staged_step(sim, handle, frames):
     # pinned buffers take the streaming form: one launch, info words arriving while the kernel runs (flagged slices),
     # decisions stored straight into the mapped host buffer; repeated to catch stale flags / cached info bytes
     info_p, pred_p = sim.pinned(frames), sim.pinned(frames)
-    os.environ["NVD_HOST_STEP"] = "streaming"        # (default: streaming only when no decisions are requested)
+    os.environ["NVD_HOST_STEP"] = "streaming"        # opt-in; the sliced form is the default
     for rep in range(3):
         info_r = np.roll(info, rep)
         info_p[:] = info_r
