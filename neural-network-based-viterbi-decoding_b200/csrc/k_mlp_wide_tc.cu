@@ -32,7 +32,7 @@ namespace {
 // 3: issue) for the NVD_WIDE_DEBUG breakdown.  The reads stay in UNCONDITIONALLY (15): they pace the issue loop, and
 // taking them out measured slower on B200 — 10^6 windows of the 200-500x4-2 decoder: 2.77 ms with all four,
 // 2.85 ms with only the stage-full pair (4), 2.95 ms with none (0) or any other single one; __nanosleep after each
-// stage instead is too coarse (3.25 ms).
+// stage instead is too coarse (3.25 ms); polling with test_wait instead of try_wait changes nothing either way.
 #ifndef NVD_WIDE_TIMING_ALWAYS
 #define NVD_WIDE_TIMING_ALWAYS 15
 #endif
