@@ -296,6 +296,14 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(1) << 46;                                // [46,48) descriptor version 1 (Blackwell)
   return d;                                                           // base_offset 0, lbo_mode 0, layout NONE (0)
 }
+// The same descriptor from a pre-shifted base: addr16 = (shared address of a 16-byte aligned base) >> 4, plus a byte
+// offset known at compile time.  All fields are disjoint and a shared-window address is < 2^18, so the whole low word
+// is ONE add on the uniform datapath instead of add / shift / mask / or per descriptor.
+__device__ __forceinline__ uint64_t make_smem_desc16(uint32_t addr16, uint32_t byte_off, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = addr16 + ((byte_off >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16));
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 // Instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
