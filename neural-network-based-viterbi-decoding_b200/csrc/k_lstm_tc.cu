@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
       ptx::bar_sync(1 + g, 128);
       if (issuer_warp && ptx::elect_one()) {
         ptx::tc_fence_after();
-        const uint32_t wbase = sbase + (dec ? kCellBytes : 0);
+        const uint32_t wbase16 = (sbase >> 4) + (dec ? (kCellBytes >> 4) : 0);   // one uniform add per descriptor
 #pragma unroll
         for (int j = 0; j < KP / 16; ++j)
           ptx::umma_f16_ts(tmem_grp + COL_D, tmem_grp + COL_A + 8 * j,
-                           ptx::make_smem_desc(wbase + j * 2 * (N * 16), N * 16, 128), idesc, j > 0);
+                           ptx::make_smem_desc16(wbase16, j * 2 * (N * 16), N * 16, 128), idesc, j > 0);
         ptx::umma_commit(bar_mma);
       }
       // next window of inputs while the MMA runs (every 32 steps; the hand-off barrier above separates it from
