@@ -346,7 +346,7 @@ def main():
                 "ms_per_step": e2e_ms,
                 "counters_only": None if e2e_co_ms is None else {"value": world * frames * L / (e2e_co_ms * 1e-3) / 1e9, "ms_per_step": e2e_co_ms,
                                                                  "d2h_bytes_per_step": 32, "note": "same call with pred_host = NULL"},
-                "api": "nvd_mc_run_host, NVD_MC_FUSED: info words H2D -> fused tcgen05 kernel -> decisions + counters D2H, sliced, copies overlapped on two copy streams, pinned host buffers"},
+                "api": "nvd_mc_run_host, NVD_MC_FUSED, pinned host buffers: ONE launch of the fused tcgen05 kernel; info words arrive by sliced H2D copies while it runs (flag per slice), decisions leave by D2H copies queued as the kernel reports slices complete; counters D2H (sliced launches instead under a profiler)"},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "ber": ber, "frame_errors": int(total_counts[0, 1]), "frames_total": int(total_counts[0, 2]),

@@ -183,9 +183,11 @@ int nvd_mc_run(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host,
 /* synchronous host-buffer form (the end-to-end call): info words come from the host, hard
  * decisions and counters go back.  info_host [B, ceil(L/8)], pred_host [B] uint8 class indices
  * (may be NULL), counters_host uint64[4] (overwritten).  Pass pinned host buffers (nvd_host_alloc).
- * NVD_MC_STAGED runs the five staged kernels per chunk; NVD_MC_FUSED runs the fused tcgen05 kernel over
- * slices of the frame range, the host<->device copies of neighbouring slices overlapping it on two
- * copy streams (1 B per frame each way).  Both give identical decisions and counters. */
+ * NVD_MC_STAGED runs the five staged kernels per chunk; NVD_MC_FUSED runs the fused tcgen05 kernel:
+ * with pinned buffers ONE launch, the info words streaming in and the decisions streaming out in
+ * slices while it runs (1 B per frame each way); otherwise (pageable buffers, NVD_HOST_STEP=sliced,
+ * or under a profiler) one launch per slice with the copies of neighbouring slices on two copy
+ * streams.  All forms give identical decisions and counters. */
 int nvd_mc_run_host(nvd_ctx* ctx, const nvd_mc_config* cfg, float snr_db, int snr_idx,
                     const uint8_t* info_host, uint8_t* pred_host, uint64_t* counters_host);
 /* per-stage device milliseconds of the most recent staged nvd_mc_run chunk sequence:

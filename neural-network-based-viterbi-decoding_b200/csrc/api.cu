@@ -10,6 +10,8 @@
 
 #include <sched.h>
 
+#include <time.h>
+
 #include "common.cuh"
 
 namespace nvd {
@@ -149,6 +151,8 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   for (cudaEvent_t e : ctx->slice_ev) cudaEventDestroy(e);
   cudaFree(ctx->slice_flags);
+  cudaFree(ctx->slice_done);
+  if (ctx->done_flags) cudaFreeHost(ctx->done_flags);
   if (ctx->slice_ones) cudaFreeHost(ctx->slice_ones);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -688,25 +692,66 @@ int nvd_mc_stage_ms(nvd_ctx* ctx, float* ms5) {
   return NVD_OK;
 }
 
-// Host-buffer step on the fused kernel: the frames are cut into slices; slice i's info words travel host->device
-// on the copy-in stream while the kernel of slice i-1 runs on the context's stream and the decisions of slice
-// i-2 travel back on the copy-out stream (events order the three).  Per frame 1 B crosses PCIe each way.
-// Streaming form of the host-buffer step: ONE launch of the fused kernel over the whole frame range.  The info words
-// arrive while it runs — sliced host->device copies on the copy-in stream, each followed by a 4-byte copy that raises
-// the slice's flag, which the kernel's producer warps wait for (the copy engines do not depend on SM resources, so
-// the kernel cannot starve them) — and the decisions are stored straight into the caller's pinned host buffer
-// (mapped memory, 1 B per frame over PCIe).  No per-slice launch prologue / tail, no copy-out stream.
+// Host-buffer step on the fused kernel, two forms.
+// Sliced: the frames are cut into slices; slice i's info words travel host->device on the copy-in stream while the
+// kernel of slice i-1 runs on the context's stream and the decisions of slice i-2 travel back on the copy-out stream
+// (events order the three).  Per frame 1 B crosses PCIe each way.
+// Streaming: ONE launch of the fused kernel over the whole frame range.  The info words arrive while it runs — a few
+// geometrically growing host->device copies on the copy-in stream, each followed by a 4-byte copy that raises the
+// slice's flag, which the kernel's producer warps wait for (the copy engines do not depend on SM resources, so the
+// kernel cannot starve them).  The decisions go to device memory; the kernel counts finished tiles per output slice
+// and raises a flag in mapped host memory when a slice is complete, and the host queues that slice's device->host
+// copy at once, under the rest of the kernel.  No per-slice launch prologue / tail.
+// The streaming step runs ONE kernel that waits for copies issued beside it.  That is fine on a plain run, but a
+// profiler that replays a kernel (ncu --set full) restores the flag words between passes without re-running the
+// copies, and the kernel's bounded wait then aborts the pass — so under a CUDA tools injection the sliced form runs.
+static bool streaming_default() {
+  static const bool v = [] {
+    for (const char* name : {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_TPS_LAUNCH_TOKEN",
+                             "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NSYS_PROFILING_SESSION_ID"})
+      if (getenv(name) != nullptr) return false;
+    return true;
+  }();
+  return v;
+}
+
 static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m, float snr_db, int snr_idx,
-                                 const uint8_t* info_host, uint8_t* pred_dev_visible, uint64_t* counters_host) {
-  const uint64_t frames = cfg->frames;
-  const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * 4 * 128;
-  uint64_t slice = 4 * wave;                                        // short slices: the first one gates the start
-  while ((frames + slice - 1) / slice > static_cast<uint64_t>(nvd_ctx::kMaxSlices)) slice *= 2;
-  const size_t n_slices = static_cast<size_t>((frames + slice - 1) / slice);
+                                 const uint8_t* info_host, uint8_t* pred_host, uint64_t* counters_host) {
+  const int64_t frames = static_cast<int64_t>(cfg->frames);
+  const int64_t wave = static_cast<int64_t>(ctx->sm_count) * 4 * 128;
+  // Input slices grow geometrically: the first (4 waves) gates the start of the kernel; slice i may be as large as
+  // the link can deliver while the kernel works through slices 0..i-1 (assumed: the link moves info bytes 1.5x
+  // faster than the kernel consumes them — 25 GB/s against 16.7 GB/s; a faster link only adds slack).
+  // Output slices shrink towards the end: only the last one's copy is exposed after the kernel.
+  HostStepSlices sl;
+  {
+    int64_t done = 0;
+    while (done < frames && sl.n_in < HostStepSlices::kMax) {
+      int64_t n = (4 + done / wave / 2) * wave;
+      if (sl.n_in == HostStepSlices::kMax - 1 || done + n > frames) n = frames - done;
+      done += n;
+      sl.in_end[sl.n_in++] = done;
+    }
+    int64_t sizes[HostStepSlices::kMax];
+    int n_out = 0;
+    int64_t left = frames, w = 6;
+    while (left > 0 && n_out < HostStepSlices::kMax) {
+      int64_t n = w * wave;
+      if (n_out == HostStepSlices::kMax - 1 || n > left) n = left;
+      sizes[n_out++] = n;
+      left -= n;
+      w = w * 8 / 5 + 1;
+    }
+    int64_t end = 0;
+    for (int i = n_out - 1; i >= 0; --i) { end += sizes[i]; sl.out_end[sl.n_out++] = end; }   // largest first
+  }
   if (!ctx->slice_flags) {
     NVD_CUDA(cudaMalloc(&ctx->slice_flags, nvd_ctx::kMaxSlices * sizeof(uint32_t)));
+    NVD_CUDA(cudaMalloc(&ctx->slice_done, nvd_ctx::kMaxSlices * sizeof(uint32_t)));
     NVD_CUDA(cudaMallocHost(&ctx->slice_ones, sizeof(uint32_t)));
     *ctx->slice_ones = 1u;
+    NVD_CUDA(cudaHostAlloc(&ctx->done_flags, nvd_ctx::kMaxSlices * sizeof(uint32_t), cudaHostAllocMapped));
+    NVD_CUDA(cudaHostGetDevicePointer(&ctx->done_flags_dev, ctx->done_flags, 0));
   }
   while (ctx->slice_ev.size() < 1) {
     cudaEvent_t e;
@@ -714,24 +759,62 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
     ctx->slice_ev.push_back(e);
   }
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  NVD_TRY(ensure_mc_buf(ctx, al(frames)));
+  NVD_TRY(ensure_mc_buf(ctx, 2 * al(frames)));
   uint8_t* d_info = static_cast<uint8_t*>(ctx->mc_buf);
+  uint8_t* d_pred = pred_host ? d_info + al(frames) : nullptr;
+  volatile uint32_t* done = ctx->done_flags;
+  for (int s = 0; s < sl.n_out; ++s) done[s] = 0u;                  // the previous call has completed (synchronous API)
   NVD_CUDA(cudaMemsetAsync(ctx->counters_scratch, 0, 4 * sizeof(uint64_t), ctx->stream));
-  NVD_CUDA(cudaMemsetAsync(ctx->slice_flags, 0, n_slices * sizeof(uint32_t), ctx->stream));
+  NVD_CUDA(cudaMemsetAsync(ctx->slice_flags, 0, HostStepSlices::kMax * sizeof(uint32_t), ctx->stream));
+  NVD_CUDA(cudaMemsetAsync(ctx->slice_done, 0, HostStepSlices::kMax * sizeof(uint32_t), ctx->stream));
   NVD_CUDA(cudaEventRecord(ctx->slice_ev[0], ctx->stream));          // flags cleared (and earlier work done) before
   NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->slice_ev[0], 0));  // the first slice may land
-  // the copies are queued BEFORE the kernel that waits for them: a tool that makes launches synchronous (ncu) must
-  // not be able to park the host inside the launch with the copies still unissued
-  for (size_t s = 0; s < n_slices; ++s) {
-    const uint64_t off = s * slice, n = std::min<uint64_t>(slice, frames - off);
+  // the copies are queued BEFORE the kernel that waits for them: a tool that makes launches synchronous must not be
+  // able to park the host inside the launch with the copies still unissued
+  for (int s = 0; s < sl.n_in; ++s) {
+    const int64_t off = s ? sl.in_end[s - 1] : 0, n = sl.in_end[s] - off;
     NVD_CUDA(cudaMemcpyAsync(d_info + off, info_host + off, n, cudaMemcpyHostToDevice, ctx->copy_in));
     NVD_CUDA(cudaMemcpyAsync(ctx->slice_flags + s, ctx->slice_ones, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in));
   }
-  NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, frames,
-                              ctx->counters_scratch, d_info, pred_dev_visible, ctx->slice_flags, static_cast<int64_t>(slice)));
+  NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, cfg->frames,
+                              ctx->counters_scratch, d_info, d_pred, ctx->slice_flags, &sl,
+                              pred_host ? ctx->slice_done : nullptr, ctx->done_flags_dev));
   NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  int next = 0;
+  const bool trace = getenv("NVD_HOST_STEP_TRACE") != nullptr;      // diagnostics: host-side timeline of this call
+  auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  const double t_launch = trace ? now_us() : 0.0;
+  double t_flag[HostStepSlices::kMax] = {0};
+  auto copy_out_slice = [&](int s) {
+    const int64_t off = s ? sl.out_end[s - 1] : 0, n = sl.out_end[s] - off;
+    return cudaMemcpyAsync(pred_host + off, d_pred + off, n, cudaMemcpyDeviceToHost, ctx->copy_out);
+  };
+  if (pred_host) {
+    // the kernel raises done[s] when every tile of output slice s has stored its decisions; that slice's
+    // device->host copy goes out at once, under the rest of the kernel.  The loop ends early if the kernel does
+    // (abort, or a tool that ran it to completion inside the launch call): the rest is copied after the sync below.
+    for (unsigned spins = 0; next < sl.n_out;) {
+      if (done[next] != 0u) { if (trace) t_flag[next] = now_us(); NVD_CUDA(copy_out_slice(next)); ++next; continue; }
+      if ((++spins & 0x3FFu) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  const double t_loop = trace ? now_us() : 0.0;
   NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
-  NVD_TRY(nvd_sync(ctx));
+  const int st = nvd_sync(ctx);
+  if (st != NVD_OK) return st;
+  const double t_sync = trace ? now_us() : 0.0;
+  if (pred_host) {
+    for (; next < sl.n_out; ++next) NVD_CUDA(copy_out_slice(next));
+    NVD_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  }
+  if (trace) {
+    fprintf(stderr, "host step trace (us after launch): flags");
+    for (int s = 0; s < sl.n_out; ++s) fprintf(stderr, " %.0f", t_flag[s] - t_launch);
+    fprintf(stderr, " | loop end %.0f | kernel synced %.0f | copies synced %.0f\n", t_loop - t_launch, t_sync - t_launch, now_us() - t_launch);
+  }
   for (int i = 0; i < 4; ++i) counters_host[i] = ctx->counters_pinned[i];
   return NVD_OK;
 }
@@ -742,26 +825,19 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
   if (!ctx->copy_in) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
   if (!ctx->copy_out) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   {
-    // the streaming form needs buffers the device can reach: pinned info words (so that the sliced copies are truly
-    // asynchronous) and decisions in mapped pinned memory (or none)
+    // the streaming form needs pinned host buffers (truly asynchronous sliced copies in both directions)
     cudaPointerAttributes ia{}, pa{};
     const bool info_pinned = cudaPointerGetAttributes(&ia, info_host) == cudaSuccess && ia.type == cudaMemoryTypeHost;
-    bool pred_ok = pred_host == nullptr;
-    uint8_t* pred_dev = nullptr;
-    if (pred_host && cudaPointerGetAttributes(&pa, pred_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
-      pred_ok = true;
-      pred_dev = static_cast<uint8_t*>(pa.devicePointer);
-    }
+    const bool pred_ok = pred_host == nullptr ||
+                         (cudaPointerGetAttributes(&pa, pred_host) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on some drivers
-    // measured (2^24 frames, 1 B200): counters only 1.185 ms streaming vs 1.205 ms sliced; with decisions 1.365 ms
-    // streaming (1-byte stores into mapped host memory are slow over PCIe) vs 1.229 ms sliced.  The sliced form is
-    // the default: a 1.7 % gain does not pay for a kernel that waits on copies issued beside it (a profiler that
-    // replays the kernel restores the flags but not the copies; the bounded wait then aborts the launch).
-    // NVD_HOST_STEP=streaming opts in.
+    // NVD_HOST_STEP=streaming|sliced chooses; see streaming_default() for the default
     const char* force = getenv("NVD_HOST_STEP");
-    const bool want = force && strcmp(force, "streaming") == 0;
+    // measured (2^24 frames, 1 B200, wall clock of the call): with decisions 1.153 ms streaming vs 1.232 ms sliced,
+    // counters only 1.117 vs 1.202 ms -> streaming is the default for pinned buffers
+    const bool want = force ? strcmp(force, "streaming") == 0 : streaming_default();
     if (want && info_pinned && pred_ok && cfg->frames > 0)
-      return mc_run_host_streaming(ctx, cfg, m, snr_db, snr_idx, info_host, pred_dev, counters_host);
+      return mc_run_host_streaming(ctx, cfg, m, snr_db, snr_idx, info_host, pred_host, counters_host);
   }
   const uint64_t frames = cfg->frames;
   // 128 frames per tile, 4 tile streams per SM: slices of a whole number of waves keep the tails small.  The first

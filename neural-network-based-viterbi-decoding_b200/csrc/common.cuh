@@ -100,6 +100,9 @@ struct nvd_ctx {
   std::vector<cudaEvent_t> slice_ev;
   uint32_t* slice_flags = nullptr;       // device: one word per input slice of the streaming host step
   uint32_t* slice_ones = nullptr;        // pinned: the value copied into a flag
+  uint32_t* slice_done = nullptr;        // device: finished tiles per output slice
+  uint32_t* done_flags = nullptr;        // mapped pinned: slice s of the decisions is complete in device memory
+  uint32_t* done_flags_dev = nullptr;    // ... its device-side address
   static constexpr int kMaxSlices = 1024;
   // staged-pipeline stage timing
   cudaEvent_t stage_ev[6] = {nullptr};
@@ -146,8 +149,17 @@ int launch_mlp_tc_staged(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y
 // fused: frames [frame0, frame0+frames) generated on chip, counters accumulated
 // info != nullptr: the info words come from that device buffer (one byte per frame) and the decisions go to
 // pred (one byte per frame, may be null) instead of being a function of the frame index
+// streaming host step: the info words arrive in n_in slices (slice i = frames [in_end[i-1], in_end[i]), valid once
+// slice_flags[i] != 0) and the decisions are counted complete in n_out slices (slice_done / done_flags); every
+// boundary except the last is a multiple of 128 frames
+struct HostStepSlices {
+  static constexpr int kMax = 16;
+  int n_in = 0, n_out = 0;
+  int64_t in_end[kMax] = {0}, out_end[kMax] = {0};
+};
 int launch_mlp_tc_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, float sigma, int snr_idx,
                         uint64_t frame0, uint64_t frames, uint64_t* counters, const uint8_t* info = nullptr,
-                        uint8_t* pred = nullptr, const uint32_t* slice_flags = nullptr, int64_t slice_frames = 0);
+                        uint8_t* pred = nullptr, const uint32_t* slice_flags = nullptr, const HostStepSlices* slices = nullptr,
+                        uint32_t* slice_done = nullptr, uint32_t* done_flags = nullptr);
 
 }  // namespace nvd

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmTcParams
       ptx::bar_sync(1 + g, 128);
       if (issuer_warp && ptx::elect_one()) {
         ptx::tc_fence_after();
-        const uint32_t wbase16 = (sbase >> 4) + (dec ? (kCellBytes >> 4) : 0);   // one uniform add per descriptor
+        const uint32_t wbase16 = ((sbase & 0x3FFFFu) >> 4) + (dec ? (kCellBytes >> 4) : 0);   // one uniform add per descriptor
 #pragma unroll
         for (int j = 0; j < KP / 16; ++j)
           ptx::umma_f16_ts(tmem_grp + COL_D, tmem_grp + COL_A + 8 * j,

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_layer_kernel(const WideP
                                (ks | j) != 0);
 #else
               ptx::umma_f16_ts(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
-                               ptx::make_smem_desc(sbase + s * kStageBytes + j * 2 * (nc * 16), nc * 16, 128), idesc,
+                               ptx::make_smem_desc16(((sbase & 0x3FFFFu) >> 4) + s * (kStageBytes >> 4), j * 2 * (nc * 16), nc * 16, 128), idesc,
                                (ks | j) != 0);
 #endif
             if (CLUSTER == 1) ptx::umma_commit(bar_empty + 8 * s);          // stage free once these MMAs have read it
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wide_pair_kernel(const WidePa
 #pragma unroll
               for (int j = 0; j < kStageK / 16; ++j)
                 ptx::umma_f16_ts_pair(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
-                                      ptx::make_smem_desc(sbase + s * kPairStageBytes + j * 2 * (64 * 16), 64 * 16, 128), idesc,
+                                      ptx::make_smem_desc16(((sbase & 0x3FFFFu) >> 4) + s * (kPairStageBytes >> 4), j * 2 * (64 * 16), 64 * 16, 128), idesc,
                                       (ks | j) != 0);
               ptx::umma_commit_pair(bar_empty + 8 * s, 3);
               if (dbg) t_i += clock64() - tt;

@@ -296,7 +296,8 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(1) << 46;                                // [46,48) descriptor version 1 (Blackwell)
   return d;                                                           // base_offset 0, lbo_mode 0, layout NONE (0)
 }
-// The same descriptor from a pre-shifted base: addr16 = (shared address of a 16-byte aligned base) >> 4, plus a byte
+// The same descriptor from a pre-shifted base: addr16 = ((shared address of a 16-byte aligned base) & 0x3FFFF) >> 4
+// (the mask matters in a cluster: the shared-window address of a non-zero rank carries high bits), plus a byte
 // offset known at compile time.  All fields are disjoint and a shared-window address is < 2^18, so the whole low word
 // is ONE add on the uniform datapath instead of add / shift / mask / or per descriptor.
 __device__ __forceinline__ uint64_t make_smem_desc16(uint32_t addr16, uint32_t byte_off, uint32_t lbo_bytes, uint32_t sbo_bytes) {
