@@ -38,6 +38,8 @@ int ensure_scratch(nvd_ctx* ctx, size_t bytes) {
   return NVD_OK;
 }
 
+constexpr size_t kTailBytes = 4 * sizeof(uint64_t) + sizeof(uint64_t);   // counters + abort flag (padded)
+
 static int check_abort(nvd_ctx* ctx) {
   if (ctx->abort_flag_host && *ctx->abort_flag_host) {
     const int code = *ctx->abort_flag_host;
@@ -47,6 +49,16 @@ static int check_abort(nvd_ctx* ctx) {
     return NVD_ERR_DEVICE_TIMEOUT;
   }
   return NVD_OK;
+}
+
+// host-buffer steps: counters and abort flag in one device->host copy queued behind the kernel(s) ...
+static cudaError_t queue_tail_copy(nvd_ctx* ctx) {
+  return cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, kTailBytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+// ... and its completion (replaces nvd_sync, which would queue a second copy for the flag alone)
+static int finish_tail(nvd_ctx* ctx) {
+  NVD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return check_abort(ctx);
 }
 
 static float sigma_of_db(float snr_db) {
@@ -113,11 +125,15 @@ int nvd_ctx_create(int device, uint64_t seed, nvd_ctx** out) {
   ctx->cc_minor = prop.minor;
   ctx->total_mem = prop.totalGlobalMem;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->abort_flag, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(ctx->abort_flag, 0, sizeof(int));
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->abort_flag_host, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->counters_scratch, 4 * sizeof(uint64_t));
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->counters_pinned, 4 * sizeof(uint64_t));
+  // the four scratch counters and the abort flag sit next to each other on both sides, so that the host-buffer
+  // steps bring both back with ONE small copy behind the kernel (kTailBytes)
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->counters_scratch, kTailBytes);
+  if (e == cudaSuccess) e = cudaMemset(ctx->counters_scratch, 0, kTailBytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->counters_pinned, kTailBytes);
+  if (e == cudaSuccess) {
+    ctx->abort_flag = reinterpret_cast<int*>(ctx->counters_scratch + 4);
+    ctx->abort_flag_host = reinterpret_cast<int*>(ctx->counters_pinned + 4);
+  }
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->stage_ev[i]);
   if (e != cudaSuccess) {
     set_error("context creation failed: %s", cudaGetErrorString(e));
@@ -142,9 +158,7 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
   for (auto& m : ctx->lstms) { cudaFree(m.blob); cudaFree(m.tc_image); }
   cudaFree(ctx->scratch);
   cudaFree(ctx->mc_buf);
-  cudaFree(ctx->abort_flag);
-  cudaFree(ctx->counters_scratch);
-  if (ctx->abort_flag_host) cudaFreeHost(ctx->abort_flag_host);
+  cudaFree(ctx->counters_scratch);                        // the abort flag lives in the same blocks
   if (ctx->counters_pinned) cudaFreeHost(ctx->counters_pinned);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   for (int i = 0; i < 6; ++i)
@@ -779,7 +793,7 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
   NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, cfg->frames,
                               ctx->counters_scratch, d_info, d_pred, ctx->slice_flags, &sl,
                               pred_host ? ctx->slice_done : nullptr, ctx->done_flags_dev));
-  NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NVD_CUDA(queue_tail_copy(ctx));
   int next = 0;
   const bool trace = getenv("NVD_HOST_STEP_TRACE") != nullptr;      // diagnostics: host-side timeline of this call
   auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
@@ -803,7 +817,7 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
   }
   const double t_loop = trace ? now_us() : 0.0;
   NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
-  const int st = nvd_sync(ctx);
+  const int st = finish_tail(ctx);
   if (st != NVD_OK) return st;
   const double t_sync = trace ? now_us() : 0.0;
   if (pred_host) {
@@ -886,10 +900,10 @@ static int mc_run_host_fused(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpModel* m
       NVD_CUDA(cudaMemcpyAsync(pred_host + off, d_pred + off, n, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
   }
-  NVD_CUDA(cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NVD_CUDA(queue_tail_copy(ctx));
   NVD_CUDA(cudaStreamSynchronize(ctx->copy_out));
   NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
-  NVD_TRY(nvd_sync(ctx));
+  NVD_TRY(finish_tail(ctx));
   for (int i = 0; i < 4; ++i) counters_host[i] = ctx->counters_pinned[i];
   return NVD_OK;
 }
