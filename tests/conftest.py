@@ -31,3 +31,10 @@ def lib():
     """The ctypes binding of libnvd.so (fails loudly when the library is not built)."""
     from nvd import _lib
     return _lib
+
+
+@pytest.fixture(scope="session")
+def golden_fwd():
+    """Outputs of the reference's own decoder graph functions run under the numpy `tensorflow`
+    stand-in (tools/gen_golden_forward.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_forward.npz"), allow_pickle=False)

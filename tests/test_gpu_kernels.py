@@ -447,3 +447,62 @@ def test_mlp_wide_single_row_and_empty(sim):
     want = omlp.forward(y, m.Ws, m.bs, m.acts, dtype=np.float64)
     assert np.abs(soft_b.download(np.float32, (1, 2)) - want).max() <= 2e-2
     sim.mlp_forward(h, sim.to_device(y), "f32", 0, 2, "bf16", want_soft=False, hard_bytes=4)      # B = 0 is a no-op
+
+
+# ------------------------------------------------------------------ reference-run golden outputs (parity pins)
+import golden_models as gm  # noqa: E402
+
+_GOLDEN_NETS = [("fnn", gm.fnn, "fnn_x"), ("mixed", gm.fnn, "mixed_x"), ("bitwise", gm.bitwise, "bitwise_x"),
+                ("seq", gm.seq_predict, "seq_x")]
+
+
+@pytest.mark.parametrize("name,builder,x_key", _GOLDEN_NETS)
+def test_mlp_fp32_matches_reference_graph(sim, golden_fwd, name, builder, x_key):
+    """The fp32 CUDA path against soft outputs the REFERENCE'S OWN multilayer_perceptron / build_network produced
+    (tools/gen_golden_forward.py) on reference-made noisy inputs with identical weights: 1e-5 relative,
+    hard decisions identical except where the top-2 margin is below 1e-3 (north-star criteria)."""
+    from nvd import weights
+    Ws, bs, acts = builder(int(golden_fwd[f"{name}_seed"]))
+    h = sim.load_mlp(weights.MlpModel(Ws, bs, acts))
+    x = golden_fwd[x_key].astype(np.float32)
+    ref, ref_pred = golden_fwd[f"{name}_out"], golden_fwd[f"{name}_pred"]
+    pred, soft = sim.decode(h, x, "fp32")
+    assert np.abs(soft - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    ok = omlp.top2_margin(ref) >= 1e-3
+    assert ok.sum() > 0.5 * len(ok) and (pred[ok] == ref_pred[ok]).all()
+
+
+@pytest.mark.parametrize("name,builder,x_key", _GOLDEN_NETS)
+def test_mlp_tensor_core_matches_reference_graph(sim, golden_fwd, name, builder, x_key):
+    """The bf16 tcgen05 paths (fused FNN kernel, wide-layer kernel, K-streamed bitwise kernel) against the same
+    reference-run outputs: 2e-2 absolute; decisions identical where the margin exceeds twice that."""
+    from nvd import weights
+    Ws, bs, acts = builder(int(golden_fwd[f"{name}_seed"]))
+    h = sim.load_mlp(weights.MlpModel(Ws, bs, acts))
+    assert sim.mlp_tc_supported(h)
+    x = golden_fwd[x_key].astype(np.float32)
+    ref, ref_pred = golden_fwd[f"{name}_out"], golden_fwd[f"{name}_pred"]
+    pred, soft = sim.decode(h, x, "bf16")
+    scale = max(1.0, np.abs(ref).max())       # ReLU logits of the bitwise net are not bounded by 1
+    assert np.abs(soft - ref).max() <= 2e-2 * scale
+    ok = omlp.top2_margin(ref) >= 5e-2 * scale
+    assert ok.sum() > 0.3 * len(ok) and (pred[ok] == ref_pred[ok]).all()
+
+
+@pytest.mark.parametrize("fast_math,tol", [(0, 2e-5), (2, 3e-2)])
+def test_lstm_matches_reference_wiring(sim, golden_fwd, fast_math, tol):
+    """K4 against the logits of the reference's build_seq2seq_model wiring (teacher-forced, 200 + 200 steps)."""
+    from nvd import weights
+    p = gm.rnn(int(golden_fwd["rnn_seed"]))
+    bits, enc = golden_fwd["rnn_bits"].astype(np.float32), golden_fwd["rnn_enc"].astype(np.float32)
+    B, L = bits.shape
+    _, dec_in, _ = olstm.prepare_batch(2.0 * bits - 1.0, enc, L)
+    h = sim.load_lstm(weights.LstmModel(**p))
+    logits_b, hard_b = sim.lstm_forward(h, sim.to_device(enc), "f32", sim.to_device(dec_in.astype(np.float32)), 2 * L, 2 * L, B,
+                                        fast_math=fast_math)
+    got = logits_b.download(np.float32, (B, 2 * L))
+    ref = golden_fwd["rnn_logits"]
+    assert np.abs(got - ref).max() <= tol
+    hard = np.unpackbits(hard_b.download(np.uint8, (B, 25)), axis=1, bitorder="little")[:, : 2 * L]
+    ok = np.abs(ref) >= (1e-3 if fast_math == 0 else 5e-2)
+    assert (hard[ok] == (ref > 0)[ok]).all()

@@ -148,3 +148,52 @@ def test_window_extraction(golden):
     # get_single_instance(8, coded, info, 6): window coded[6:14], label = info[3]
     assert golden["gsi_x"].tolist() == list(range(6, 14))
     assert golden["gsi_y"].tolist() == [0.0, 1.0]
+
+
+# ---- decoder forward: the oracle against the reference's OWN graph functions (tools/gen_golden_forward.py) ----
+import golden_models as gm  # noqa: E402
+from oracle import mlp as omlp  # noqa: E402
+
+
+@pytest.mark.parametrize("name,builder,x_key", [("fnn", gm.fnn, "fnn_x"), ("mixed", gm.fnn, "mixed_x"),
+                                                ("bitwise", gm.bitwise, "bitwise_x"), ("seq", gm.seq_predict, "seq_x")])
+def test_mlp_forward_matches_reference_graph(golden_fwd, name, builder, x_key):
+    """multilayer_perceptron / build_network of the reference (run under the numpy tf stand-in, fp32) against
+    oracle.mlp.forward with the same parameters: soft outputs within 1e-5, decisions equal off ties."""
+    Ws, bs, acts = builder(int(golden_fwd[f"{name}_seed"]))
+    x = golden_fwd[x_key].astype(np.float32)
+    ref = golden_fwd[f"{name}_out"]
+    got = omlp.forward(x, Ws, bs, acts, dtype=np.float64)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    ok = omlp.top2_margin(got) >= 1e-5
+    assert (omlp.argmax_first(got)[ok] == golden_fwd[f"{name}_pred"][ok]).all()
+    got32 = omlp.forward(x, Ws, bs, acts, dtype=np.float32)
+    assert np.abs(got32 - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_bitwise_graph_shape_quirk(golden_fwd):
+    # Wout is [n_hidden_1, 2]: the h2..h4 layers are created but not wired (src/fnn_viterbi_bitwise.py:371-397)
+    assert golden_fwd["bitwise_wout_shape"].tolist() == [30, 2]
+    assert (golden_fwd["bitwise_out"] >= 0).all()               # ReLU on the logits
+    assert np.abs(golden_fwd["bitwise_x"]).max() <= 4           # int32-truncated channel output (:309-317)
+
+
+def test_seq_windows_match_reference(golden_fwd):
+    # get_single_instance (src/fnn_viterbi_seq_predict.py:293-336): window i = stream[2i : 2i + 200], label = info[i]
+    s, info = golden_fwd["seq_stream"], golden_fwd["seq_info"]
+    for i in range(golden_fwd["seq_x"].shape[0]):
+        assert np.array_equal(golden_fwd["seq_x"][i], s[2 * i:2 * i + 200].astype(np.float32))
+        assert golden_fwd["seq_labels_onehot"][i].argmax() == info[i]
+
+
+def test_lstm_forward_matches_reference_wiring(golden_fwd):
+    """build_seq2seq_model's wiring (encoder over y, decoder from the encoder's final state over the teacher-forced
+    inputs, linear head) run by the reference's own code; the cell arithmetic is the stand-in's TF-1.x LSTMCell."""
+    p = gm.rnn(int(golden_fwd["rnn_seed"]))
+    bits, enc = golden_fwd["rnn_bits"].astype(np.float64), golden_fwd["rnn_enc"].astype(np.float64)
+    _, dec_in, dec_tgt = lstm.prepare_batch(2.0 * bits - 1.0, enc, 100)
+    got = lstm.seq2seq_forward(enc, dec_in, p, dtype=np.float64)
+    assert np.abs(got - golden_fwd["rnn_logits"]).max() <= 1e-5
+    assert float(np.mean((dec_tgt - got) ** 2)) == pytest.approx(float(golden_fwd["rnn_loss"]), rel=1e-5)
+    assert not golden_fwd["rnn_prediction"].any()               # argmax over a size-1 axis (B-12)
