@@ -100,7 +100,8 @@ int nvd_encode(nvd_ctx* ctx, int code, const uint8_t* info_packed, int L, int64_
 
 /* ---- K2 channel: replaces modulate_awgn (src/fnn_viterbi.py:224-253) + the per-frame Python
  * loops that call it (:380-388).  y[b, j] = (2c-1) + sigma * N(0,1), noise = Philox4x32-10 keyed
- * by (seed; frame0+b, j/4, snr_idx).  y is [B, n] dense in out_dtype (NVD_F32/BF16/I32_TRUNC). */
+ * by (seed; frame0+b, j/6, snr_idx) — six symbols per Philox call.  y is [B, n] dense in out_dtype
+ * (NVD_F32/BF16/I32_TRUNC). */
 int nvd_channel(nvd_ctx* ctx, const uint8_t* coded_packed, int n, int64_t B, float sigma,
                 int snr_idx, uint64_t frame0, int out_dtype, void* y);
 

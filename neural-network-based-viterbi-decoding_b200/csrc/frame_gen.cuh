@@ -1,7 +1,7 @@
 // frame_gen.cuh — device functions shared by the staged kernels (K0/K1/K2) and the fused
 // pipeline kernel, so that both produce bit-identical frames:
 //   * Philox4x32-10 counter-based generator (checked word-for-word against oracle/philox.py)
-//   * Box–Muller on MUFU (lg2 / sqrt / sin / cos approximations)
+//   * Box–Muller on MUFU (lg2 / sqrt / sin / cos approximations), six normals per Philox call
 //   * shift-XOR convolutional encoder on time-packed words
 //       encode_133171  /root/reference/src/fnn_viterbi.py:157-217  taps {0,2,3,5,6} / {0,1,2,3,6}
 //       encode_57      /root/reference/src/fnn_viterbi.py:122-154  taps {0,2} / {0,1,2}, g=5 first,
@@ -78,56 +78,65 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
-// two 32-bit words -> two N(0,1) draws (float64 statement: oracle/philox.py box_muller); four MUFU
-// operations per pair: lg2, sqrt, sin, cos
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float th = __int2float_rn(static_cast<int>(b)) * 1.4629180792671596e-9f;  // pi * 2^-31
-  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u1));               // sqrt(-2 ln u1)
-  z0 = r * __cosf(th);
-  z1 = r * __sinf(th);
+// One Philox call (128 bits) feeds SIX symbols (oracle/philox.py block_normals): three Box-Muller pairs, pair i
+// taking a 27-bit radius uniform from the top of word i and a 15-bit angle made of the low 5 bits of word i and bits
+// [10i, 10i+10) of word 3.  Four MUFU operations per pair: lg2, sqrt, cos, sin.
+constexpr int kNormalsPerBlock = 6;
+
+// radius / angle fields of pair i (0..2) of a block
+__device__ __forceinline__ float bm_log2_u1(uint32_t xi) {          // lg2((r_bits + 0.5) * 2^-27)
+  return __log2f(fmaf(__uint2float_rn(xi >> 5), 7.450580596923828e-9f, 3.725290298461914e-9f));
+}
+template <int I>
+__device__ __forceinline__ float bm_theta(uint32_t xi, uint32_t x3) {   // int32(a_bits << 17) * pi * 2^-31
+  const uint32_t lo = (I == 0) ? (x3 << 17) : (I == 1) ? (x3 << 7) : (x3 >> 3);
+  uint32_t t;
+  asm("lop3.b32 %0, %1, 0x07FE0000, %2, 0xEA;" : "=r"(t) : "r"(lo), "r"(xi << 27));   // (lo & mask) | (xi << 27)
+  return __int2float_rn(static_cast<int>(t)) * 1.4629180792671596e-9f;                 // pi * 2^-31
 }
 
-// 4 standard normals of symbols 4*block .. 4*block+3 of `frame`
-__device__ __forceinline__ void noise4(uint64_t seed, uint64_t frame, uint32_t block,
-                                       uint32_t stream_word, float z[4]) {
-  const uint4 x = frame_words(seed, frame, block, stream_word);
-  box_muller(x.x, x.y, z[0], z[1]);
-  box_muller(x.z, x.w, z[2], z[3]);
-}
-
-__device__ __forceinline__ void noise4(const PhiloxKeys& rk, uint64_t frame, uint32_t block,
-                                       uint32_t stream_word, float z[4]) {
-  const uint4 x = frame_words(rk, frame, block, stream_word);
-  box_muller(x.x, x.y, z[0], z[1]);
-  box_muller(x.z, x.w, z[2], z[3]);
-}
-
-// 8 standard normals of symbols 4*block .. 4*block+7: the same arithmetic as two noise4 calls, written
-// stage by stage (both Philox chains, then all lg2, all sqrt, all sin/cos) so that the MUFU
-// operations of the four Box-Muller pairs are in flight together instead of queueing one by one.
-__device__ __forceinline__ void box_muller8(const uint4 x0, const uint4 x1, float z[8]);
-__device__ __forceinline__ void noise8(uint64_t seed, uint64_t frame, uint32_t block,
-                                       uint32_t stream_word, float z[8]) {
-  box_muller8(frame_words(seed, frame, block, stream_word), frame_words(seed, frame, block + 1, stream_word), z);
-}
-__device__ __forceinline__ void noise8(const PhiloxKeys& rk, uint64_t frame, uint32_t block,
-                                       uint32_t stream_word, float z[8]) {
-  box_muller8(frame_words(rk, frame, block, stream_word), frame_words(rk, frame, block + 1, stream_word), z);
-}
-__device__ __forceinline__ void box_muller8(const uint4 x0, const uint4 x1, float z[8]) {
-  const uint32_t a[4] = {x0.x, x0.z, x1.x, x1.z};
-  const uint32_t b[4] = {x0.y, x0.w, x1.y, x1.w};
-  float l[4], th[4], r[4];
+// the first NP (1..3) pairs of one block -> z[0 .. 2*NP); written stage by stage (all lg2, all sqrt, all sin/cos) so
+// that the MUFU operations of the pairs are in flight together instead of queueing one by one
+template <int NP>
+__device__ __forceinline__ void block_normals(const uint4 x, float* z) {
+  const uint32_t w[3] = {x.x, x.y, x.z};
+  float l[NP], th[NP], r[NP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    l[i] = __log2f(fmaf(__uint2float_rn(a[i]), 2.3283064365386963e-10f, 1.1641532182693481e-10f));
-    th[i] = __int2float_rn(static_cast<int>(b[i])) * 1.4629180792671596e-9f;
+  for (int i = 0; i < NP; ++i) l[i] = bm_log2_u1(w[i]);
+  th[0] = bm_theta<0>(w[0], x.w);
+  if constexpr (NP > 1) th[1] = bm_theta<1>(w[1], x.w);
+  if constexpr (NP > 2) th[2] = bm_theta<2>(w[2], x.w);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);   // sqrt(-2 ln u1)
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    z[2 * i] = r[i] * __cosf(th[i]);
+    z[2 * i + 1] = r[i] * __sinf(th[i]);
   }
+}
+
+// 6 standard normals of symbols 6*block .. 6*block+5 of `frame`
+__device__ __forceinline__ void noise6(const PhiloxKeys& rk, uint64_t frame, uint32_t block, uint32_t stream_word, float z[6]) {
+  block_normals<3>(frame_words(rk, frame, block, stream_word), z);
+}
+
+// the 14 normals of an L = 7 frame (blocks 0, 1 and the first pair of block 2): the three Philox chains first, then
+// the seven Box-Muller pairs stage by stage
+__device__ __forceinline__ void noise14(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, float z[14]) {
+  const uint4 x0 = frame_words(rk, frame, 0u, stream_word);
+  const uint4 x1 = frame_words(rk, frame, 1u, stream_word);
+  const uint4 x2 = frame_words(rk, frame, 2u, stream_word);
+  const uint32_t w[7] = {x0.x, x0.y, x0.z, x1.x, x1.y, x1.z, x2.x};
+  float l[7], th[7], r[7];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);
+  for (int i = 0; i < 7; ++i) l[i] = bm_log2_u1(w[i]);
+  th[0] = bm_theta<0>(x0.x, x0.w); th[1] = bm_theta<1>(x0.y, x0.w); th[2] = bm_theta<2>(x0.z, x0.w);
+  th[3] = bm_theta<0>(x1.x, x1.w); th[4] = bm_theta<1>(x1.y, x1.w); th[5] = bm_theta<2>(x1.z, x1.w);
+  th[6] = bm_theta<0>(x2.x, x2.w);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 7; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
     z[2 * i] = r[i] * __cosf(th[i]);
     z[2 * i + 1] = r[i] * __sinf(th[i]);
   }

@@ -3,11 +3,11 @@
 // Replaces modulate_awgn (/root/reference/src/fnn_viterbi.py:224-253: x = float32(c), 0 -> -1,
 // y = x + np.random.normal(0, sigma)) and the per-frame Python loops that call it
 // (:380-388; fnn_viterbi_mixed_snr.py:452-460; fnn_viterbi_bitwise.py:309-317).  The noise of
-// symbol j of global frame f is Philox4x32-10(key = seed, counter = (f, j/4, snr_idx|stream)),
-// so a frame is reproducible from (seed, SNR index, frame index) on any GPU count.
+// symbol j of global frame f is Philox4x32-10(key = seed, counter = (f, j/6, snr_idx|stream)) — six symbols per
+// Philox call (frame_gen.cuh) — so a frame is reproducible from (seed, SNR index, frame index) on any GPU count.
 //
-// One thread = one (frame, 4-symbol block): 1 Philox call, 2 Box–Muller pairs, 4 outputs.
-// Consecutive threads write consecutive 4-symbol groups -> coalesced.  Algorithmic HBM traffic
+// One thread = one (frame, 6-symbol block): 1 Philox call, 3 Box–Muller pairs, 6 outputs.
+// Consecutive threads write consecutive 6-symbol groups -> coalesced.  Algorithmic HBM traffic
 // per frame: ceil(n/8) B read + n*s B written (s = 2 bf16, 4 fp32/int32): 30 B / 58 B at n=14.
 #include "common.cuh"
 #include "frame_gen.cuh"
@@ -44,35 +44,32 @@ __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const
   if (kSmall) f = static_cast<uint32_t>(t) / static_cast<uint32_t>(nblk);
   else f = t / nblk;
   const int blk = static_cast<int>(t - f * nblk);
-  const int j0 = 4 * blk;
-  const uint32_t bits = (static_cast<uint32_t>(__ldg(coded + f * S + (j0 >> 3))) >> (j0 & 7)) & 0xFu;
-  float z[4];
-  noise4(rk, frame0 + f, blk, stream_word, z);
-  float v[4];
+  const int j0 = kNormalsPerBlock * blk;
+  const uint8_t* cb = coded + f * S + (j0 >> 3);
+  uint32_t two = __ldg(cb);
+  if ((j0 >> 3) + 1 < S) two |= static_cast<uint32_t>(__ldg(cb + 1)) << 8;
+  const uint32_t bits = (two >> (j0 & 7)) & 0x3Fu;
+  float z[6];
+  noise6(rk, frame0 + f, blk, stream_word, z);
+  float v[6];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = fmaf(sigma, z[k], ((bits >> k) & 1u) ? 1.0f : -1.0f);
+  for (int k = 0; k < 6; ++k) v[k] = fmaf(sigma, z[k], ((bits >> k) & 1u) ? 1.0f : -1.0f);
   T* row = y + f * n + j0;
-  if (j0 + 4 <= n && (n & 1) == 0) {
-    // even n: rows start 4 B (bf16) / 8 B (fp32, int32) aligned -> two vector stores
-    if constexpr (kDtype == NVD_BF16) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
-      reinterpret_cast<__nv_bfloat162*>(row)[0] = lo;
-      reinterpret_cast<__nv_bfloat162*>(row)[1] = hi;
-    } else if constexpr (kDtype == NVD_F32) {
-      reinterpret_cast<float2*>(row)[0] = make_float2(v[0], v[1]);
-      reinterpret_cast<float2*>(row)[1] = make_float2(v[2], v[3]);
-    } else {
-      reinterpret_cast<int2*>(row)[0] = make_int2(cast_out<kDtype>(v[0]), cast_out<kDtype>(v[1]));
-      reinterpret_cast<int2*>(row)[1] = make_int2(cast_out<kDtype>(v[2]), cast_out<kDtype>(v[3]));
+  if (j0 + 6 <= n && (n & 1) == 0) {
+    // even n: rows start 4 B (bf16) / 8 B (fp32, int32) aligned -> three vector stores
+#pragma unroll
+    for (int k = 0; k < 6; k += 2) {
+      if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + k)[0] = __floats2bfloat162_rn(v[k], v[k + 1]);
+      else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + k)[0] = make_float2(v[k], v[k + 1]);
+      else reinterpret_cast<int2*>(row + k)[0] = make_int2(cast_out<kDtype>(v[k]), cast_out<kDtype>(v[k + 1]));
     }
   } else {
-    for (int k = 0; k < 4 && j0 + k < n; ++k) row[k] = cast_out<kDtype>(v[k]);
+    for (int k = 0; k < 6 && j0 + k < n; ++k) row[k] = cast_out<kDtype>(v[k]);
   }
 }
 
 // Short frames (n <= 16 symbols, n even: the class decoders, L <= 8): one thread = one frame, the same
-// two noise8 calls as the fused pipeline's producer warps — 4 Philox blocks and 7-8 Box-Muller pairs per thread
+// noise generation as the fused pipeline's producer warps — 3 Philox blocks and 7-8 Box-Muller pairs per thread
 // with no per-block index arithmetic (2.3x fewer instructions per frame than the block-per-thread kernel).
 // A warp's 32 rows are contiguous in y, so its 4- / 8-byte stores fill whole sectors between them.
 // kN: compile-time symbol count (14 for the reference L = 7: the unused Box-Muller pair and every bound check
@@ -95,21 +92,22 @@ __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk,
   uint32_t bits = live ? __ldg(coded + f * S) : 0u;
   if (live && S > 1) bits |= static_cast<uint32_t>(__ldg(coded + f * S + 1)) << 8;
   T* row = &stage[wib][lane * n];
+  float z[18];
+  if (kN == 14) {
+    noise14(rk, frame0 + f, stream_word, z);
+  } else {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (8 * half >= n) break;
-    float z[8];
-    noise8(rk, frame0 + f, 2 * half, stream_word, z);
+    for (int blk = 0; blk < 3; ++blk)
+      if (kNormalsPerBlock * blk < n) noise6(rk, frame0 + f, blk, stream_word, z + kNormalsPerBlock * blk);
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = 8 * half + 2 * i;
-      if (j >= n) break;
-      const float a = fmaf(sigma, z[2 * i], ((bits >> j) & 1u) ? 1.0f : -1.0f);
-      const float b = fmaf(sigma, z[2 * i + 1], ((bits >> (j + 1)) & 1u) ? 1.0f : -1.0f);
-      if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(a, b);
-      else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + j)[0] = make_float2(a, b);
-      else reinterpret_cast<int2*>(row + j)[0] = make_int2(cast_out<kDtype>(a), cast_out<kDtype>(b));
-    }
+  for (int j = 0; j < 16; j += 2) {
+    if (j >= n) break;
+    const float a = fmaf(sigma, z[j], ((bits >> j) & 1u) ? 1.0f : -1.0f);
+    const float b = fmaf(sigma, z[j + 1], ((bits >> (j + 1)) & 1u) ? 1.0f : -1.0f);
+    if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(a, b);
+    else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + j)[0] = make_float2(a, b);
+    else reinterpret_cast<int2*>(row + j)[0] = make_int2(cast_out<kDtype>(a), cast_out<kDtype>(b));
   }
   __syncwarp();
   const int64_t rows = (B - f_warp < 32) ? (B - f_warp) : 32;
@@ -124,7 +122,7 @@ __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk,
 int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float sigma, int snr_idx,
                    uint64_t frame0, int out_dtype, void* y) {
   if (B == 0) return NVD_OK;
-  const int S = (n + 7) / 8, nblk = (n + 3) / 4;
+  const int S = (n + 7) / 8, nblk = (n + kNormalsPerBlock - 1) / kNormalsPerBlock;
   const int64_t threads = B * nblk;
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
   const uint32_t sw = noise_stream_word(snr_idx);

@@ -12,7 +12,13 @@ Counter / key convention shared with the CUDA side (csrc/frame_gen.cuh):
     key     = (seed & 0xffffffff, seed >> 32)
     counter = (frame & 0xffffffff, frame >> 32, block, (snr_idx << 8) | stream)
     stream  = STREAM_NOISE (1) for channel noise, STREAM_INFO (2) for source bits
-One call yields 4 words = the noise of symbols 4*block .. 4*block+3 (or 128 source bits).
+One call yields 4 words = 128 source bits, or the noise of SIX symbols 6*block .. 6*block+5: three
+Box-Muller pairs, pair i taking a 27-bit radius uniform from the top of word i and a 15-bit angle made of
+the low 5 bits of word i and bits [10i, 10i+10) of word 3 (42 bits per pair; the top two bits of word 3
+are unused).  27 bits put the largest radius at sqrt(2 * 28 * ln 2) = 6.23 sigma; 2^15 directions keep the
+angular lattice (1.9e-4 rad) far below the bf16 rounding of the stored symbol.  (Round 1 spent a whole
+32-bit word on each of radius and angle: 4 symbols per call; the Philox rounds are the dominant cost of
+every Monte-Carlo kernel, so the same 128 bits now feed 6.)
 """
 from __future__ import annotations
 
@@ -60,31 +66,40 @@ def frame_words(seed: int, stream_word: int, frames: np.ndarray, block: int):
     )
 
 
-def box_muller(a: np.ndarray, b: np.ndarray):
-    """Two uint32 words -> two N(0,1) draws, float64 statement of csrc/frame_gen.cuh:
-        u1 = (a + 0.5) * 2^-32   in (0,1)
-        th = int32(b) * pi * 2^-31   in [-pi, pi)
+NORMALS_PER_BLOCK = 6
+
+
+def box_muller(r_bits: np.ndarray, a_bits: np.ndarray):
+    """27-bit radius field, 15-bit angle field -> two N(0,1) draws; float64 statement of
+    csrc/frame_gen.cuh:
+        u1 = (r_bits + 0.5) * 2^-27            in (0,1)
+        th = int32(a_bits << 17) * pi * 2^-31  in [-pi, pi)
         r  = sqrt(-2 ln u1);  z0 = r cos th;  z1 = r sin th
     """
-    u1 = (a.astype(np.float64) + 0.5) * 2.0 ** -32
-    th = b.astype(np.int32).astype(np.float64) * (np.pi * 2.0 ** -31)
+    u1 = (r_bits.astype(np.float64) + 0.5) * 2.0 ** -27
+    th = (a_bits.astype(np.uint32) << np.uint32(17)).astype(np.int32).astype(np.float64) * (np.pi * 2.0 ** -31)
     r = np.sqrt(-2.0 * np.log(u1))
     return r * np.cos(th), r * np.sin(th)
+
+
+def block_normals(x0, x1, x2, x3):
+    """Philox words of one call -> [.., 6] normals (symbols 6*block .. 6*block+5)."""
+    out = []
+    for i, xi in enumerate((x0, x1, x2)):
+        r_bits = xi >> np.uint32(5)
+        a_bits = ((xi & np.uint32(31)) << np.uint32(10)) | ((x3 >> np.uint32(10 * i)) & np.uint32(1023))
+        out.extend(box_muller(r_bits, a_bits))
+    return np.stack(out, axis=-1)
 
 
 def noise_normals(seed: int, snr_idx: int, frames: np.ndarray, n: int) -> np.ndarray:
     """N(0,1) noise matrix [len(frames), n] (float64) for the given global frame indices."""
     frames = np.asarray(frames, dtype=np.uint64)
-    out = np.empty((frames.shape[0], 4 * ((n + 3) // 4)), dtype=np.float64)
+    nblk = (n + NORMALS_PER_BLOCK - 1) // NORMALS_PER_BLOCK
+    out = np.empty((frames.shape[0], NORMALS_PER_BLOCK * nblk), dtype=np.float64)
     sw = ((snr_idx & 0xFFFFFF) << 8) | STREAM_NOISE
-    for blk in range((n + 3) // 4):
-        x0, x1, x2, x3 = frame_words(seed, sw, frames, blk)
-        z0, z1 = box_muller(x0, x1)
-        z2, z3 = box_muller(x2, x3)
-        out[:, 4 * blk + 0] = z0
-        out[:, 4 * blk + 1] = z1
-        out[:, 4 * blk + 2] = z2
-        out[:, 4 * blk + 3] = z3
+    for blk in range(nblk):
+        out[:, 6 * blk:6 * blk + 6] = block_normals(*frame_words(seed, sw, frames, blk))
     return out[:, :n]
 
 

@@ -30,3 +30,24 @@ def test_normals_are_standard_and_reproducible():
 def test_info_bits_balanced():
     b = philox.info_bits(philox.DEFAULT_SEED, np.arange(4096, dtype=np.uint64), 518)
     assert b.shape == (4096, 518) and abs(b.mean() - 0.5) < 5e-3
+
+
+def test_six_normals_per_block_are_gaussian_and_independent():
+    """One Philox call feeds three Box-Muller pairs (27-bit radius, 15-bit angle each): marginals, tails,
+    independence within a pair / across pairs of a block, and across blocks."""
+    from scipy import stats
+    f = np.arange(1 << 18, dtype=np.uint64)
+    z = philox.noise_normals(philox.DEFAULT_SEED, 1, f, 18)               # three whole blocks
+    assert stats.kstest(z[:, 0], "norm").pvalue > 1e-3 and stats.kstest(z[:, 5], "norm").pvalue > 1e-3
+    n = z.size
+    for t, p in ((2.0, 4.55e-2), (3.0, 2.70e-3), (4.0, 6.33e-5)):
+        k = (np.abs(z) > t).sum()
+        assert abs(k - n * p) < 5 * np.sqrt(n * p)                        # two-sided tail mass
+    c = np.corrcoef(z.T)
+    assert np.abs(c - np.eye(18)).max() < 1e-2                            # symbols of a frame are uncorrelated
+    assert abs(np.corrcoef(z[:, 0] ** 2, z[:, 1] ** 2)[0, 1]) < 1e-2      # ... and the pair's squares (radius shared!)
+    # the three pairs of a block share word 3 only through disjoint bit fields
+    x = philox.frame_words(philox.DEFAULT_SEED, (1 << 8) | philox.STREAM_NOISE, f[:8], 0)
+    zz = philox.block_normals(*x)
+    assert np.allclose(zz, z[:8, :6])
+    assert np.abs(z).max() < 6.24                                         # 27-bit radius: sqrt(2 * 28 * ln 2)
