@@ -60,6 +60,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.active, self.stop_flag = index, [], set(), False, False
+        self.power = []
         self.max_mhz, self.ok = None, False
         try:
             import pynvml
@@ -80,6 +81,10 @@ class ClockSampler(threading.Thread):
                 mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 if self.active:
                     self.samples.append(float(mhz))
+                    try:
+                        self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    except Exception:
+                        pass
                     for bit, name in self.REASONS.items():
                         if mask & bit:
                             self.reasons.add(name)
@@ -87,11 +92,18 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.005)
 
+    def reset(self):
+        self.samples, self.power, self.reasons = [], [], set()
+
     def summary(self):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": float(np.median(self.samples)), "sm_min_mhz": float(np.min(self.samples)), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power:
+            out["power_w_median"] = float(np.median(self.power))
+            out["power_w_max"] = float(np.max(self.power))
+        return out
 
 
 def cpu_pipeline_rate(model, frames_per_call: int, seconds_budget: float, threads=None):
@@ -119,6 +131,8 @@ def run_reference(args, rank, world):
         return 0
     from nvd import weights
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses the whole host at every N
+    torch.set_num_threads(os.cpu_count() or 1)
     model = weights.load_default_fnn()
     sample = 1 << 20                                   # bounded sample of the 2^24-frame step
     from oracle import encoders as oenc, pipeline as opipe
@@ -162,6 +176,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-staged", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="headline + e2e only (skip sustained / deep-BER / bitwise / rnn / seq legs)")
+    ap.add_argument("--deep-min-errors", type=int, default=100, help="deep-BER stop rule: frame errors per SNR point")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -175,6 +191,7 @@ def main():
         dist.init("nccl")
     model = weights.load_default_fnn()
     sim = montecarlo.Simulator(device=local if world > 1 else 0)
+    sim.comm_init(rank, world)                          # the library's own NCCL communicator (nvd_comm_init)
     h = sim.load_mlp(model)
     frames = args.frames
     frame0 = rank * frames                              # weak scaling: every rank owns its own 2^24-frame range per step
@@ -188,27 +205,30 @@ def main():
     counters = sim.zeros(32)
     for w in range(args.warmup):
         sim.run_async(h, "133171", L, [SNR_DB], frames, counters, frame0 + w * world * frames, mode="fused")
+    sim.allreduce_counters(counters, 4)                 # warm the communicator's first-use set-up
     sim.sync()
     counters = sim.zeros(32)
     dist.barrier()
     sim.sync()
-    e0, e1 = sim.event(), sim.event()
+    e0, e1, e2 = sim.event(), sim.event(), sim.event()
     sampler.active = True
     sim.record(e0)
     for s in range(args.steps):
         sim.run_async(h, "133171", L, [SNR_DB], frames, counters, frame0 + s * world * frames, mode="fused")
     sim.record(e1)
+    # the path's one exchange step: ncclAllReduce(sum, uint64[4]) on the library's stream, directly on the device
+    # counters, queued behind the last launch (no host bounce) — inside the timed region
+    sim.allreduce_counters(counters, 4)
+    sim.record(e2)
     sim.sync()
-    fused_ms = sim.elapsed_ms(e0, e1)
-    t_ar = time.perf_counter()
-    local_counts = counters.download(np.uint64, (1, 4))
-    total_counts = dist.all_reduce_sum(local_counts.astype(np.int64)).astype(np.uint64) if world > 1 else local_counts
-    ar_ms = (time.perf_counter() - t_ar) * 1e3 if world > 1 else 0.0
+    fused_ms = sim.elapsed_ms(e0, e2)
+    ar_ms = sim.elapsed_ms(e1, e2) if world > 1 else 0.0
+    kernels_ms = sim.elapsed_ms(e0, e1)
+    total_counts = counters.download(np.uint64, (1, 4))
     sampler.active = False
     dist.barrier()
-    step_ms_local = (fused_ms + ar_ms) / args.steps
-    step_ms = dist.all_reduce_max(step_ms_local)
-    kernel_ms = dist.all_reduce_max(fused_ms / args.steps)
+    step_ms = dist.all_reduce_max(fused_ms / args.steps)
+    kernel_ms = dist.all_reduce_max(kernels_ms / args.steps)
     value = world * frames * L / (step_ms * 1e-3) / 1e9
 
     # ---------------- end to end: host buffers through nvd_mc_run_host -------------------------------
@@ -251,34 +271,164 @@ def main():
         staged["total_ms"] = sum(ms.values())
         staged["gbit_per_s"] = frames * L / (staged["total_ms"] * 1e-3) / 1e9
 
-    # ---------------- BASELINE.json configs[3]: rnn_viterbi LSTM seq2seq, (133,171) L = 100 blocks (K4-tc) -----------
+    clocks = sampler.summary()             # clocks of the headline timed region only
+
+    # ---------------- sustained: >= 3 s of back-to-back fused launches (clock / power state over seconds) -----------
+    sustained = None
+    if not args.no_legs:
+        n_sus = max(int(3200.0 / max(step_ms, 1e-3)), 100)
+        c_sus = sim.zeros(32)
+        sampler.reset()
+        dist.barrier()
+        sampler.active = True
+        sim.record(e0)
+        for s_ in range(n_sus):
+            sim.run_async(h, "133171", L, [SNR_DB], frames, c_sus, frame0 + (args.steps + s_) * world * frames, mode="fused")
+        sim.allreduce_counters(c_sus, 4)
+        sim.record(e1)
+        sim.sync()
+        sampler.active = False
+        sus_ms = dist.all_reduce_max(sim.elapsed_ms(e0, e1))
+        sus_tflops = FLOP_PER_FRAME * frames * n_sus / (sus_ms * 1e-3) / 1e12
+        sustained = {"launches": n_sus, "seconds": sus_ms * 1e-3, "value": world * frames * n_sus * L / (sus_ms * 1e-3) / 1e9, "unit": UNIT,
+                     "ms_per_step": sus_ms / n_sus, "tflops_per_gpu": sus_tflops,
+                     "frac_of_bf16_sustained_peak": sus_tflops / peaks["bf16_sustained"], "clocks": sampler.summary()}
+
+    # ---------------- BASELINE.json configs[4]: deep-BER run with the stop rule, one C-ABI call (nvd_mc_sweep) ------
+    deep = None
+    if not args.no_legs:
+        deep_db = [5.0, 6.0, 7.0, 8.0]
+        dist.barrier()
+        t0 = time.perf_counter()
+        dc = sim.sweep(h, "133171", L, deep_db, min_frame_errors=args.deep_min_errors, max_frames=1 << 34,
+                       chunk_frames=world << 26, mode="fused", world=world)
+        deep_s = dist.all_reduce_max(time.perf_counter() - t0)
+        pts = []
+        for db_, c_ in zip(deep_db, dc):
+            lo_, hi_ = montecarlo.wilson(float(c_[0]), float(c_[3]))
+            pts.append({"snr_db": db_, "frames": int(c_[2]), "bit_errors": int(c_[0]), "frame_errors": int(c_[1]),
+                        "ber": float(c_[0]) / max(float(c_[3]), 1.0), "fer": float(c_[1]) / max(float(c_[2]), 1.0), "ber_ci95": [lo_, hi_]})
+        tot_frames = int(dc[:, 2].sum())
+        deep = {"workload": "configs[4]: (133,171) FNN deep-BER, stop at >= %d frame errors per point or 2^34 frames, "
+                            "chunks of 2^26 frames per GPU, counters all-reduced in the library after every chunk" % args.deep_min_errors,
+                "points": pts, "frames_total": tot_frames, "seconds": deep_s, "gbit_per_s": tot_frames * L / deep_s / 1e9,
+                "frac_of_headline": tot_frames * L / deep_s / 1e9 / value}
+
+    # ---------------- BASELINE.json configs[2]: per-bit predictor + mixed-SNR decoder, 0..8 dB, frames sharded over ranks --
+    sweep_db = [float(d) for d in range(0, 9)]
+    bitwise = None
+    if not args.no_legs:
+        from nvd import weights as _wb
+        mb = _wb.load_default_bitwise()
+        hb = sim.load_mlp(mb)
+        fb = 1 << 21                                       # frames per SNR point per GPU
+        cb_ = sim.zeros(32 * len(sweep_db))
+        sim.run_bitwise_async(hb, 512, [2.0], 1 << 16, cb_, 0, mode="fused")       # warm
+        sim.sync()
+        cb_ = sim.zeros(32 * len(sweep_db))
+        dist.barrier()
+        sim.record(e0)
+        sim.run_bitwise_async(hb, 512, sweep_db, fb, cb_, rank * fb, mode="fused", trunc=True)
+        sim.allreduce_counters(cb_, 4 * len(sweep_db))
+        sim.record(e1)
+        sim.sync()
+        bw_ms = dist.all_reduce_max(sim.elapsed_ms(e0, e1))
+        cbw = cb_.download(np.uint64, (len(sweep_db), 4))
+        n_fr = world * fb * len(sweep_db)
+        bitwise = {"workload": "configs[2]: fnn_viterbi_bitwise 1036-30-2 (ReLU) predictor of bit 0, L=512 + 6 state bits, "
+                               "int32-truncated channel (reference data sets), 0..8 dB, fused K-streamed tcgen05 pipeline",
+                   "frames_per_point_per_gpu": fb, "ms": bw_ms, "mframes_per_s": n_fr / (bw_ms * 1e-3) / 1e6,
+                   "decoded_mbit_per_s": n_fr / (bw_ms * 1e-3) / 1e6, "gnormals_per_s": n_fr * 1036 / (bw_ms * 1e-3) / 1e9,
+                   "tflops": n_fr * 62280 / (bw_ms * 1e-3) / 1e12,
+                   "bit_error_rate": [float(c_[0]) / max(float(c_[3]), 1.0) for c_ in cbw], "weights": mb.meta.get("path", "seed-fixed init")}
+        if world == 1:                                     # staged: per-stage HBM rates (algorithmic bytes)
+            sim.set_stage_timing(True)
+            cs_ = sim.zeros(32)
+            fs_ = 1 << 18
+            for _ in range(2):
+                sim.run_bitwise_async(hb, 512, [2.0], fs_, cs_, 0, mode="staged", trunc=True)
+            msb = sim.stage_ms()
+            sim.set_stage_timing(False)
+            algb = {"source": 64 + 64 + 65, "encode": 65 + 130, "channel": 130 + 2072, "decode": 2072 + 1, "count": 1 + 1}
+            bitwise["staged"] = {k: {"ms": msb[k], "GB/s": algb[k] * fs_ / (msb[k] * 1e-3) / 1e9 if msb[k] > 0 else None,
+                                     "frac_of_hbm": algb[k] * fs_ / (msb[k] * 1e-3) / 1e9 / peaks["hbm_gbs"] if msb[k] > 0 else None}
+                                 for k in msb}
+            bitwise["staged"]["frames"] = fs_
+            bitwise["staged"]["mframes_per_s"] = fs_ / (sum(msb.values()) * 1e-3) / 1e6
+
+    mixed = None
+    if not args.no_legs:
+        cm_ = sim.zeros(32 * len(sweep_db))
+        dist.barrier()
+        sim.record(e0)
+        sim.run_async(h, "133171", L, sweep_db, frames, cm_, frame0, mode="fused")
+        sim.allreduce_counters(cm_, 4 * len(sweep_db))
+        sim.record(e1)
+        sim.sync()
+        mx_ms = dist.all_reduce_max(sim.elapsed_ms(e0, e1))
+        cmx = cm_.download(np.uint64, (len(sweep_db), 4))
+        mixed = {"workload": "configs[2]: fnn_viterbi_mixed_snr decoder (one model trained over -2..9 dB) tested at 0..8 dB, "
+                             "2^24 frames per point per GPU, one all-reduce for the sweep",
+                 "ms": mx_ms, "gbit_per_s": world * frames * len(sweep_db) * L / (mx_ms * 1e-3) / 1e9,
+                 "ber": [float(c_[0]) / max(float(c_[3]), 1.0) for c_ in cmx], "fer": [float(c_[1]) / max(float(c_[2]), 1.0) for c_ in cmx]}
+
+    # ---------------- BASELINE.json configs[3]: rnn_viterbi as a Monte-Carlo pipeline (nvd_mc_run_lstm) ---------------
     other = None
-    if not args.no_staged and world == 1:
-        from nvd import weights as _w, _lib as _l
-        Hh, Ll, Bl = 20, 100, info["sm_count"] * 5 * 128
-        rng = np.random.default_rng(4)
-        lim = float(np.sqrt(6.0 / (1 + Hh + 4 * Hh)))
-        lp = {"enc_W": rng.uniform(-lim, lim, (1 + Hh, 4 * Hh)), "enc_b": np.zeros(4 * Hh), "dec_W": rng.uniform(-lim, lim, (1 + Hh, 4 * Hh)),
-              "dec_b": np.zeros(4 * Hh), "lin_w": rng.uniform(-0.5, 0.5, Hh), "lin_b": np.zeros(1)}
-        hl = sim.load_lstm(_w.LstmModel(**{k: v.astype(np.float32) for k, v in lp.items()}))
-        d_y = sim.to_device(rng.standard_normal((Bl, 2 * Ll)).astype(np.float32))
-        d_hard = sim.alloc(Bl * 25)
-        def lstm_step(mode):
-            _l.check(sim.lib.nvd_lstm_forward(sim.ctx, hl, d_y.ptr, _l.DTYPES["f32"], None, 2 * Ll, 2 * Ll, Bl, mode, None, d_hard.ptr))
-        other = {"workload": "configs[3]: rnn_viterbi LSTM(20) seq2seq, L=100 (T=200+200), autoregressive decisions", "frames": Bl}
-        for name, mode, reps in (("fp32_pipe", 1, 2), ("tcgen05_bf16", 2, 10)):
-            lstm_step(mode); sim.sync()
-            e0, e1 = sim.event(), sim.event()
+    if not args.no_legs:
+        from nvd import weights as _w
+        lm = _w.load_default_lstm()
+        hl = sim.load_lstm(lm)
+        Ll, Bl = 100, info["sm_count"] * 5 * 128 * 4
+        other = {"workload": "configs[3]: rnn_viterbi LSTM(20) seq2seq on (133,171) L=100 blocks: Philox info -> K1 -> K2 (int32-"
+                             "truncated) -> K4 (200 + 200 steps) -> K5, frames sharded over ranks, 2 dB", "frames_per_gpu": Bl}
+        for name, fm, teacher, reps in (("tcgen05_teacher_forced", 2, True, 5), ("tcgen05_autoregressive", 2, False, 5), ("fp32_pipe_teacher_forced", 1, True, 1)):
+            cl_ = sim.zeros(32)
+            sim.run_lstm_async(hl, Ll, [2.0], Bl, cl_, rank * Bl, fast_math=fm, teacher_forced=teacher)
+            sim.sync()
+            cl_ = sim.zeros(32)
+            dist.barrier()
             sim.record(e0)
-            for _ in range(reps):
-                lstm_step(mode)
-            sim.record(e1); sim.sync()
-            ms_l = sim.elapsed_ms(e0, e1) / reps
-            other[name] = {"ms": ms_l, "gbit_per_s": Bl * Ll / (ms_l * 1e-3) / 1e9, "mframes_per_s": Bl / (ms_l * 1e-3) / 1e6}
+            for r_ in range(reps):
+                sim.run_lstm_async(hl, Ll, [2.0], Bl, cl_, (r_ * world + rank) * Bl, fast_math=fm, teacher_forced=teacher)
+            sim.allreduce_counters(cl_, 4)
+            sim.record(e1)
+            sim.sync()
+            ms_l = dist.all_reduce_max(sim.elapsed_ms(e0, e1)) / reps
+            cl = cl_.download(np.uint64, (4,))
+            other[name] = {"ms": ms_l, "gbit_per_s": world * Bl * Ll / (ms_l * 1e-3) / 1e9, "mframes_per_s": world * Bl / (ms_l * 1e-3) / 1e6,
+                           "ber": float(cl[0]) / max(float(cl[3]), 1.0)}
+        if world == 1:
+            sim.set_stage_timing(True)
+            cl_ = sim.zeros(32)
+            sim.run_lstm_async(hl, Ll, [2.0], Bl, cl_, 0, fast_math=2, teacher_forced=True)
+            other["stage_ms"] = sim.stage_ms()
+            sim.set_stage_timing(False)
+
+    # ---------------- the reference's own decode surface: predictions.eval(feed_dict={x: test_set}) on HOST arrays ------
+    decode_host = None
+    if not args.no_legs and not args.no_e2e:
+        nd = 1 << 22
+        y_host = sim.pinned(nd * 14 * 4).view(np.float32).reshape(nd, 14)
+        rng_d = np.random.default_rng(7)
+        y_host[:] = rng_d.standard_normal((nd, 14), dtype=np.float32)
+        hard_host = sim.pinned(nd * 4).view(np.int32)
+        from nvd import _lib as _ld
+        def dec_step(prec):
+            _ld.check(sim.lib.nvd_mlp_decode_host(sim.ctx, h, y_host.ctypes.data, nd, _ld.PRECISIONS[prec], None, hard_host.ctypes.data))
+        dec_step("bf16")
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dec_step("bf16")
+        dh_ms = dist.all_reduce_max((time.perf_counter() - t0) * 1e3 / 3)
+        decode_host = {"api": "nvd_mlp_decode_host (fnn_viterbi.predict): fp32 rows in pinned host memory -> int32 decisions in host memory; "
+                              "double-buffered H2D / convert + tcgen05 forward / D2H on three streams",
+                       "frames": nd, "ms": dh_ms, "value": world * nd * L / (dh_ms * 1e-3) / 1e9, "unit": UNIT,
+                       "h2d_bytes_per_step": nd * 56, "d2h_bytes_per_step": nd * 4, "h2d_gb_per_s": nd * 56 / (dh_ms * 1e-3) / 1e9}
 
     # ---------------- sliding-window decoder (fnn_viterbi_seq_predict, 200-500x4-2) on the wide-layer tcgen05 kernel ---
     seq = None
-    if not args.no_staged and world == 1:
+    if not args.no_legs and world == 1:
         from nvd import weights as _w2, _lib as _l2
         dims_s = [200, 500, 500, 500, 500, 2]
         rng = np.random.default_rng(3)
@@ -306,7 +456,6 @@ def main():
 
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
-    clocks = sampler.summary()
 
     if rank != 0:
         sim.close()
@@ -351,9 +500,15 @@ def main():
         "clocks": clocks,
         "ber": ber, "frame_errors": int(total_counts[0, 1]), "frames_total": int(total_counts[0, 2]),
         "allreduce_ms": ar_ms,
+        "comm": sim.comm_info(),
         "staged": staged,
+        "sustained": sustained,
+        "deep_ber": deep,
+        "bitwise": bitwise,
+        "mixed_snr_sweep": mixed,
         "rnn_viterbi": other,
         "seq_predict": seq,
+        "decode_host": decode_host,
         "e2e_counters": [int(x) for x in c_e2e],
     }
     print(json.dumps(line), flush=True)

@@ -52,7 +52,8 @@ typedef enum {
 enum { NVD_CODE_57_REF = 0, NVD_CODE_133171 = 1, NVD_CODE_57_CAUSAL = 2 };
 /* channel output storage — float32 rows (src/fnn_viterbi.py:373,384), bf16 for the tensor-core
  * path, or the int32 truncation of src/fnn_viterbi_bitwise.py:309-317 / src/rnn_viterbi.py:201-208 */
-enum { NVD_F32 = 0, NVD_BF16 = 1, NVD_I32_TRUNC = 2 };
+enum { NVD_F32 = 0, NVD_BF16 = 1, NVD_I32_TRUNC = 2,
+       NVD_BF16_TRUNC = 3 /* the truncated integer stored as bf16 (exact): the same quirk on the tensor-core path */ };
 /* activations — tanh src/fnn_viterbi.py:496-508, relu src/fnn_viterbi_bitwise.py:388,397 */
 enum { NVD_ACT_IDENTITY = 0, NVD_ACT_TANH = 1, NVD_ACT_RELU = 2 };
 /* arithmetic of the decoder forward */
@@ -170,7 +171,7 @@ typedef struct {
   int32_t struct_bytes;   /* = sizeof(nvd_mc_config) */
   int32_t model;          /* MLP handle */
   int32_t code;           /* NVD_CODE_* */
-  int32_t L;              /* info bits per frame (<= 16 for class decoders) */
+  int32_t L;              /* info bits per frame (<= 8: class decoders carry one info byte per frame) */
   int32_t precision;      /* NVD_PREC_* */
   int32_t mode;           /* NVD_MC_STAGED | NVD_MC_FUSED (fused needs BF16_TC + covered shape) */
   int32_t y_dtype;        /* staged: storage of the channel output (NVD_F32 / NVD_BF16) */
@@ -197,9 +198,93 @@ int nvd_mc_stage_ms(nvd_ctx* ctx, float* ms5);
 /* per-stage timing makes staged nvd_mc_run synchronise after every chunk; off by default. */
 int nvd_mc_set_stage_timing(nvd_ctx* ctx, int enabled);
 
+/* ---- Monte-Carlo step of the per-bit predictor (BASELINE.json configs[2]) ------------------------------------
+ * replaces generate_test_data (src/fnn_viterbi_bitwise.py:290-323: random info bits, encode_133171_with_state from
+ * `starting_state`, modulate_awgn into an int32 row), the test forward of build_network (:326-399) and the decision /
+ * error count against info bit `bit_position` (:456-457, :504-509).  One decoded bit per frame: counters are
+ * {bit errors, frame errors (same number), frames, bits (= frames)}.  The model is a [2(L + n_state_bits), N1 <= 64,
+ * n_out <= 8] net (nvd_mlp_tc_supported).  NVD_MC_FUSED (BF16_TC only) generates the frames on chip; NVD_MC_STAGED
+ * runs K0 (Philox info bits) -> prefix -> K1 -> K2 -> K3 -> K5 through HBM.  Both give identical counters. */
+typedef struct {
+  int32_t struct_bytes;   /* = sizeof(nvd_mc_bitwise_config) */
+  int32_t model;
+  int32_t code;           /* NVD_CODE_* */
+  int32_t L;              /* info bits per frame (block_length, 512) */
+  int32_t n_state_bits;   /* constraint_length (6): start-state bits prepended to the info bits; 0 = none */
+  int32_t state;          /* starting_state, the number extract_state_bits takes (:114-138) */
+  int32_t bit_position;   /* the info bit the net predicts */
+  int32_t precision;      /* NVD_PREC_FP32 (staged only) | NVD_PREC_BF16_TC */
+  int32_t mode;           /* NVD_MC_STAGED | NVD_MC_FUSED */
+  int32_t trunc;          /* 1 = the reference data sets' int32 truncation of the channel output (:309-317), 0 = real-valued */
+  uint64_t frame0;
+  uint64_t frames;
+} nvd_mc_bitwise_config;
+int nvd_mc_run_bitwise(nvd_ctx* ctx, const nvd_mc_bitwise_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host,
+                       int n_snr, uint64_t* counters_dev);
+
+/* ---- Monte-Carlo step of the recurrent decoder (BASELINE.json configs[3]) --------------------------------------
+ * replaces generate_datasets' test half (src/rnn_viterbi.py:186-232: random info bits, encode_133171, modulate_awgn
+ * into an int32 row), prepare_batch's teacher-forced decoder inputs (:328-377), the forward of build_seq2seq_model
+ * (:278-305) and the BER over the first L decoder steps (:471-491), with the decision bit = logit > 0 (B-12).
+ * K0 (Philox info bits) -> K1 -> K2 -> K4 (T_enc = T_dec = 2L) -> K5 on packed rows; counters as nvd_mc_run.
+ * teacher_forced = 1 feeds [EOS, info, 0...] as the reference does even at test time; 0 feeds the previous decision
+ * back.  fast_math as nvd_lstm_forward (2 = tcgen05 recurrence). */
+typedef struct {
+  int32_t struct_bytes;   /* = sizeof(nvd_mc_lstm_config) */
+  int32_t model;          /* LSTM handle */
+  int32_t code;
+  int32_t L;              /* info bits per frame (100) */
+  int32_t fast_math;      /* 0, 1, 2 */
+  int32_t teacher_forced;
+  int32_t trunc;          /* 1 = int32 truncation of the channel output (:216-222) */
+  int32_t reserved;
+  uint64_t frame0;
+  uint64_t frames;
+} nvd_mc_lstm_config;
+int nvd_mc_run_lstm(nvd_ctx* ctx, const nvd_mc_lstm_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host,
+                    int n_snr, uint64_t* counters_dev);
+
+/* K5 variants the two steps above use, also callable on their own (device buffers, counters accumulated into):
+ * decision byte (0/1) per frame against bit `bit_position` of a packed info row (src/fnn_viterbi_bitwise.py:504-509);
+ * packed decision rows against packed info rows with different strides, first L bits (src/rnn_viterbi.py:477-491). */
+int nvd_count_bit_errors(nvd_ctx* ctx, const uint8_t* pred, const uint8_t* info_packed, int info_stride_bytes, int bit_position,
+                         int64_t B, uint64_t* counters_dev);
+int nvd_count_row_errors(nvd_ctx* ctx, const uint8_t* pred_packed, int pred_stride_bytes, const uint8_t* info_packed,
+                         int info_stride_bytes, int L, int64_t B, uint64_t* counters_dev);
+/* the six start-state bits in front of every packed frame (encode_133171_with_state, src/fnn_viterbi_bitwise.py:162-163):
+ * out [B, ceil((L + n_state_bits) / 8)] */
+int nvd_prepend_state(nvd_ctx* ctx, const uint8_t* info_packed, int L, int state, int n_state_bits, int64_t B, uint8_t* out);
+
+/* ---- multi-GPU exchange step ------------------------------------------------------------------
+ * The reference is single-process; the path shards by global frame range, one context (process or
+ * thread) per GPU, and the ONLY exchange is the sum of the error counters that calculate_error / calculate_ber
+ * (src/fnn_viterbi.py:619-674, src/fnn_viterbi_mixed_snr.py:634-655) would have computed over the whole test set.
+ * It is an ncclAllReduce(ncclUint64, ncclSum) over NVLink queued on the context's stream right behind the launches
+ * that produce the counters.  NCCL is bound at run time (dlopen of libnccl.so.2; NVD_NCCL_LIB overrides): a host
+ * without NCCL can still use every single-GPU entry point.
+ *   rank 0:    nvd_comm_unique_id(id)  ->  ship the NVD_COMM_ID_BYTES bytes to the other ranks (any host channel)
+ *   all ranks: nvd_comm_init(ctx, rank, world, id)  (collective)  ...  nvd_comm_allreduce_u64  ...  nvd_comm_destroy */
+#define NVD_COMM_ID_BYTES 128
+int nvd_comm_unique_id(void* id_out);
+int nvd_comm_init(nvd_ctx* ctx, int rank, int world, const void* id);
+int nvd_comm_destroy(nvd_ctx* ctx);
+int nvd_comm_info(nvd_ctx* ctx, int* rank, int* world, int* nccl_version);
+/* in-place sum over all ranks of n uint64 values in DEVICE memory (e.g. the [n_snr][4] counters of nvd_mc_run);
+ * asynchronous on the context's stream; a no-op on a context without a communicator. */
+int nvd_comm_allreduce_u64(nvd_ctx* ctx, uint64_t* values_dev, size_t n);
+
+/* Deep-BER driver (BASELINE.json configs[4]): per SNR point, chunks of `chunk_frames` GLOBAL frames are added until
+ * the point has >= min_frame_errors frame errors (globally, after the all-reduce) or max_frames frames.  With a
+ * communicator every rank takes its contiguous share of each chunk (cfg->frame0 + done + [rank, rank+1) * chunk / world)
+ * and the counters are all-reduced after every chunk, so all ranks take the same stop decision.  Synchronous.
+ * cfg->frames is ignored.  counters_host: uint64 [n_snr][4], overwritten, identical on every rank.
+ * replaces the fixed-size test set of train_test_dataset (src/fnn_viterbi.py:380-388) as the stopping rule. */
+int nvd_mc_sweep(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host, int n_snr,
+                 uint64_t min_frame_errors, uint64_t max_frames, uint64_t chunk_frames, uint64_t* counters_host);
+
 /* ---- diagnostics ---------------------------------------------------------------------------
  * One tcgen05.mma (M=128, K=16, bf16 x bf16 -> fp32) on caller-supplied raw shared-memory images
- * and descriptor strides; used by tests/test_gpu_umma_probe.py to pin the UMMA shared-memory
+ * and descriptor strides; used by tests/test_gpu_kernels.py::test_umma_layout_probe to pin the UMMA shared-memory
  * layout the tensor-core kernel relies on.  a_image_host: 4096 B, b_image_host: N*32 B,
  * d_host: [128, N] fp32. */
 /* phase time stamps (clock64) of CTA 0's four groups over their first 64 tiles of a fused run:

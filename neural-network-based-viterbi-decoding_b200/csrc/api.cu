@@ -61,6 +61,10 @@ static int finish_tail(nvd_ctx* ctx) {
   return check_abort(ctx);
 }
 
+// NVD_BF16_TRUNC is a channel OUTPUT convention; readers see plain bf16
+static int storage_dtype(int d) { return d == NVD_BF16_TRUNC ? NVD_BF16 : d; }
+static bool known_dtype(int d) { return d == NVD_F32 || d == NVD_BF16 || d == NVD_I32_TRUNC || d == NVD_BF16_TRUNC; }
+
 static float sigma_of_db(float snr_db) {
   // sigma = sqrt(1 / (2 * 10^(dB/10)))   /root/reference/src/fnn_viterbi.py:89-92
   return static_cast<float>(std::sqrt(0.5 / std::pow(10.0, static_cast<double>(snr_db) / 10.0)));
@@ -75,6 +79,34 @@ __global__ void gather_windows_f32_kernel(const T* __restrict__ src, int64_t src
   const int64_t row = i / K;
   const int64_t s = row * stride + (i - row * K);
   out[i] = s < src_len ? static_cast<float>(src[s]) : 0.0f;
+}
+
+// any storage dtype -> bf16, element-wise (rows for the K-streamed tensor-core path)
+template <typename T>
+__global__ void to_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(static_cast<float>(in[i]));
+}
+
+// K-streamed tensor-core path over dense rows [B, K] of any storage dtype (bf16 rows are consumed in place)
+static int kstream_rows(nvd_ctx* ctx, const MlpModel& m, const void* y, int y_dtype, int64_t B, float* soft_out, void* hard_out,
+                        int hard_bytes) {
+  const int K = m.dims[0];
+  if (y_dtype == NVD_BF16) return launch_mlp_kstream(ctx, m, static_cast<const __nv_bfloat16*>(y), K, B, soft_out, hard_out, hard_bytes);
+  const int64_t pass = std::min<int64_t>(B, int64_t(1) << 18);
+  NVD_TRY(ensure_scratch(ctx, static_cast<size_t>(pass) * K * 2));
+  __nv_bfloat16* tmp = static_cast<__nv_bfloat16*>(ctx->scratch);
+  const int n_out = m.dims[m.n_layers];
+  for (int64_t r0 = 0; r0 < B; r0 += pass) {
+    const int64_t rows = std::min(pass, B - r0), n = rows * K;
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (y_dtype == NVD_F32) to_bf16_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(y) + r0 * K, tmp, n);
+    else to_bf16_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(y) + r0 * K, tmp, n);
+    NVD_CHECK_LAUNCH();
+    NVD_TRY(launch_mlp_kstream(ctx, m, tmp, K, rows, soft_out ? soft_out + r0 * n_out : nullptr,
+                               hard_out ? static_cast<char*>(hard_out) + r0 * hard_bytes : nullptr, hard_bytes));
+  }
+  return NVD_OK;
 }
 
 }  // namespace nvd
@@ -149,10 +181,13 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
   if (!ctx) return NVD_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
   for (auto& m : ctx->mlps) {
     for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m.W[l]); cudaFree(m.b[l]); }
     cudaFree(m.tc_image);
     cudaFree(m.tc_bias_out);
+    cudaFree(m.ks_image);
+    cudaFree(m.ks_l2);
     for (int l = 0; l < kMaxLayers; ++l) cudaFree(m.wide_image[l]);
   }
   for (auto& m : ctx->lstms) { cudaFree(m.blob); cudaFree(m.tc_image); }
@@ -365,6 +400,7 @@ int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts, c
   }
   if (tc_shape_supported(m)) NVD_TRY(tc_build_image(ctx, m, W_host, b_host));
   else if (wide_tc_supported(m)) NVD_TRY(wide_tc_build_image(m, W_host, b_host));
+  else if (kstream_supported(m)) NVD_TRY(kstream_build_image(m, W_host, b_host));
   ctx->mlps.push_back(m);
   *model = static_cast<int>(ctx->mlps.size()) - 1;
   return NVD_OK;
@@ -384,6 +420,8 @@ int nvd_mlp_free(nvd_ctx* ctx, int model) {
   for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->W[l]); cudaFree(m->b[l]); m->W[l] = m->b[l] = nullptr; }
   cudaFree(m->tc_image); m->tc_image = nullptr;
   cudaFree(m->tc_bias_out); m->tc_bias_out = nullptr;
+  cudaFree(m->ks_image); m->ks_image = nullptr;
+  cudaFree(m->ks_l2); m->ks_l2 = nullptr;
   for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->wide_image[l]); m->wide_image[l] = nullptr; }
   m->wide = false;
   m->live = false;
@@ -394,7 +432,7 @@ int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported) {
   NVD_REQUIRE(ctx && supported, "null argument");
   MlpModel* m;
   NVD_TRY(get_mlp(ctx, model, &m));
-  *supported = (m->tc_image || m->wide) ? 1 : 0;
+  *supported = (m->tc_image || m->wide || m->ks_image) ? 1 : 0;
   return NVD_OK;
 }
 
@@ -424,8 +462,10 @@ int nvd_window_decode(nvd_ctx* ctx, int model, const void* stream, int stream_dt
   MlpModel* m;
   NVD_TRY(get_mlp(ctx, model, &m));
   NVD_REQUIRE(stream && n_symbols >= 0 && stride >= 1 && n_windows >= 0, "bad stream / stride / window count");
-  NVD_REQUIRE(stream_dtype == NVD_F32 || stream_dtype == NVD_BF16 || stream_dtype == NVD_I32_TRUNC, "unknown stream dtype %d", stream_dtype);
+  NVD_REQUIRE(known_dtype(stream_dtype), "unknown stream dtype %d", stream_dtype);
+  stream_dtype = storage_dtype(stream_dtype);
   NVD_REQUIRE(!hard_out || hard_bytes == 1 || hard_bytes == 2 || hard_bytes == 4, "hard_bytes must be 1, 2 or 4");
+  NVD_REQUIRE(!hard_out || hard_bytes == 4 || m->dims[m->n_layers] <= (1 << (8 * hard_bytes)), "class index does not fit hard_bytes");
   const int K = m->dims[0];
   NVD_REQUIRE(n_windows == 0 || (n_windows - 1) * stride + K <= n_symbols, "windows run past the end of the stream");
   if (n_windows == 0) return NVD_OK;
@@ -461,12 +501,14 @@ int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t
   MlpModel* m;
   NVD_TRY(get_mlp(ctx, model, &m));
   NVD_REQUIRE(B >= 0 && (B == 0 || y), "bad B / null input");
-  NVD_REQUIRE(y_dtype == NVD_F32 || y_dtype == NVD_BF16 || y_dtype == NVD_I32_TRUNC, "unknown y_dtype %d", y_dtype);
+  NVD_REQUIRE(known_dtype(y_dtype), "unknown y_dtype %d", y_dtype);
+  y_dtype = storage_dtype(y_dtype);
   NVD_REQUIRE(!hard_out || hard_bytes == 1 || hard_bytes == 2 || hard_bytes == 4, "hard_bytes must be 1, 2 or 4");
   NVD_REQUIRE(!hard_out || hard_bytes == 4 || m->dims[m->n_layers] <= (1 << (8 * hard_bytes)), "class index does not fit hard_bytes");
   if (precision == NVD_PREC_FP32) return launch_mlp_fp32(ctx, *m, y, y_dtype, B, soft_out, hard_out, hard_bytes);
   if (precision == NVD_PREC_BF16_TC) {
     if (m->wide) return wide_rows(ctx, *m, y, y_dtype, B * m->dims[0], m->dims[0], B, soft_out, hard_out, hard_bytes);
+    if (m->ks_image) return kstream_rows(ctx, *m, y, y_dtype, B, soft_out, hard_out, hard_bytes);
     if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
     NVD_REQUIRE(y_dtype == NVD_BF16, "BF16_TC path takes bf16 inputs (TMA-staged activations)");
     return launch_mlp_tc_staged(ctx, *m, static_cast<const __nv_bfloat16*>(y), B, soft_out, hard_out, hard_bytes);
@@ -481,49 +523,94 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
+static int ensure_copy_streams(nvd_ctx* ctx) {
+  if (!ctx->copy_in) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  if (!ctx->copy_out) NVD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  return NVD_OK;
+}
+
+// The reference's `predictions.eval(feed_dict={x: test_set})` (src/fnn_viterbi.py:606-610) on host arrays: rows go
+// through two sets of device buffers so that the host->device copy of chunk i+1, the forward of chunk i and the
+// device->host copy of chunk i-1 overlap (copy-in stream / the context's stream / copy-out stream, ordered by events).
+// The fp32 -> bf16 conversion of the tensor-core path runs on the device.  Pageable host arrays work (the driver
+// stages them; the call that touches them blocks the host, the device keeps working); pinned ones overlap fully.
 int nvd_mlp_decode_host(nvd_ctx* ctx, int model, const float* y_host, int64_t B, int precision, float* soft_host,
                         int32_t* hard_host) {
   CTX_GUARD(ctx);
   MlpModel* m;
   NVD_TRY(get_mlp(ctx, model, &m));
   NVD_REQUIRE(B >= 0 && (B == 0 || y_host), "bad B / null input");
+  NVD_REQUIRE(precision == NVD_PREC_FP32 || precision == NVD_PREC_BF16_TC, "unknown precision %d", precision);
   if (B == 0) return NVD_OK;
+  const bool tc = precision == NVD_PREC_BF16_TC;
+  if (tc && !(m->tc_image || m->wide || m->ks_image)) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
+  NVD_TRY(ensure_copy_streams(ctx));
   const int n_in = m->dims[0], n_out = m->dims[m->n_layers];
-  const int64_t chunk = std::min<int64_t>(B, 1 << 20);
-  const size_t in_b = static_cast<size_t>(chunk) * n_in * 4, in16_b = static_cast<size_t>(chunk) * n_in * 2;
-  const size_t soft_b = soft_host ? static_cast<size_t>(chunk) * n_out * 4 : 0;
-  const size_t hard_b = static_cast<size_t>(chunk) * 4;
-  const size_t need = in_b + in16_b + soft_b + hard_b + 1024;
-  if (need > ctx->mc_buf_bytes) {
-    NVD_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->mc_buf);
-    ctx->mc_buf = nullptr; ctx->mc_buf_bytes = 0;
-    NVD_CUDA(cudaMalloc(&ctx->mc_buf, need));
-    ctx->mc_buf_bytes = need;
+  const int64_t by_bytes = (int64_t(64) << 20) / (static_cast<int64_t>(n_in) * 4);
+  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(1024, std::min<int64_t>(int64_t(1) << 18, by_bytes)));
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const bool need16 = tc && m->tc_image != nullptr;      // the fused FNN kernel takes bf16 rows; the others convert themselves
+  const size_t in_b = al(static_cast<size_t>(chunk) * n_in * 4), in16_b = need16 ? al(static_cast<size_t>(chunk) * n_in * 2) : 0;
+  const size_t soft_b = soft_host ? al(static_cast<size_t>(chunk) * n_out * 4) : 0, hard_b = hard_host ? al(static_cast<size_t>(chunk) * 4) : 0;
+  const size_t set_b = in_b + in16_b + soft_b + hard_b;
+  NVD_TRY(ensure_mc_buf(ctx, 2 * set_b));
+  while (ctx->slice_ev.size() < 6) {
+    cudaEvent_t e;
+    NVD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->slice_ev.push_back(e);
   }
-  char* base = static_cast<char*>(ctx->mc_buf);
-  float* d_in = reinterpret_cast<float*>(base);
-  __nv_bfloat16* d_in16 = reinterpret_cast<__nv_bfloat16*>(base + in_b);
-  float* d_soft = soft_host ? reinterpret_cast<float*>(base + in_b + ((in16_b + 255) & ~size_t(255))) : nullptr;
-  int32_t* d_hard = reinterpret_cast<int32_t*>(base + in_b + ((in16_b + 255) & ~size_t(255)) + ((soft_b + 255) & ~size_t(255)));
-  for (int64_t r0 = 0; r0 < B; r0 += chunk) {
-    const int64_t rows = std::min<int64_t>(chunk, B - r0);
-    NVD_CUDA(cudaMemcpyAsync(d_in, y_host + r0 * n_in, static_cast<size_t>(rows) * n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (precision == NVD_PREC_BF16_TC && m->wide) {
-      NVD_TRY(wide_rows(ctx, *m, d_in, NVD_F32, rows * n_in, n_in, rows, d_soft, hard_host ? d_hard : nullptr, 4));
-    } else if (precision == NVD_PREC_BF16_TC) {
-      if (!m->tc_image) { set_error("model %d has no tcgen05 image (shape not covered)", model); return NVD_ERR_UNSUPPORTED; }
+  // events per buffer set: [0,1] input landed, [2,3] forward done, [4,5] outputs copied out
+  cudaEvent_t* ev_in = &ctx->slice_ev[0];
+  cudaEvent_t* ev_done = &ctx->slice_ev[2];
+  cudaEvent_t* ev_out = &ctx->slice_ev[4];
+  struct Set { float* in; __nv_bfloat16* in16; float* soft; int32_t* hard; } set[2];
+  for (int k = 0; k < 2; ++k) {
+    char* base = static_cast<char*>(ctx->mc_buf) + k * set_b;
+    set[k].in = reinterpret_cast<float*>(base);
+    set[k].in16 = need16 ? reinterpret_cast<__nv_bfloat16*>(base + in_b) : nullptr;
+    set[k].soft = soft_host ? reinterpret_cast<float*>(base + in_b + in16_b) : nullptr;
+    set[k].hard = hard_host ? reinterpret_cast<int32_t*>(base + in_b + in16_b + soft_b) : nullptr;
+  }
+  // earlier work on the context's stream may still use mc_buf
+  NVD_CUDA(cudaEventRecord(ev_done[0], ctx->stream));
+  NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_done[0], 0));
+  NVD_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_done[0], 0));
+  const int64_t n_chunks = (B + chunk - 1) / chunk;
+  auto copy_out = [&](int64_t c) -> int {
+    const int k = static_cast<int>(c & 1);
+    const int64_t r0 = c * chunk, rows = std::min<int64_t>(chunk, B - r0);
+    NVD_CUDA(cudaStreamWaitEvent(ctx->copy_out, ev_done[k], 0));
+    if (soft_host) NVD_CUDA(cudaMemcpyAsync(soft_host + r0 * n_out, set[k].soft, static_cast<size_t>(rows) * n_out * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (hard_host) NVD_CUDA(cudaMemcpyAsync(hard_host + r0, set[k].hard, static_cast<size_t>(rows) * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+    NVD_CUDA(cudaEventRecord(ev_out[k], ctx->copy_out));
+    return NVD_OK;
+  };
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int k = static_cast<int>(c & 1);
+    const int64_t r0 = c * chunk, rows = std::min<int64_t>(chunk, B - r0);
+    if (c >= 2) NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_done[k], 0));          // the forward of chunk c-2 has read set k
+    NVD_CUDA(cudaMemcpyAsync(set[k].in, y_host + r0 * n_in, static_cast<size_t>(rows) * n_in * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+    NVD_CUDA(cudaEventRecord(ev_in[k], ctx->copy_in));
+    NVD_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[k], 0));
+    if (c >= 2) NVD_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out[k], 0));            // the outputs of chunk c-2 have left set k
+    if (tc && m->wide) {
+      NVD_TRY(wide_rows(ctx, *m, set[k].in, NVD_F32, rows * n_in, n_in, rows, set[k].soft, set[k].hard, 4));
+    } else if (tc && m->ks_image) {
+      NVD_TRY(kstream_rows(ctx, *m, set[k].in, NVD_F32, rows, set[k].soft, set[k].hard, 4));
+    } else if (tc) {
       const int64_t n = rows * n_in;
-      f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_in16, n);
+      f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(set[k].in, set[k].in16, n);
       NVD_CHECK_LAUNCH();
-      NVD_TRY(launch_mlp_tc_staged(ctx, *m, d_in16, rows, d_soft, hard_host ? d_hard : nullptr, 4));
+      NVD_TRY(launch_mlp_tc_staged(ctx, *m, set[k].in16, rows, set[k].soft, set[k].hard, 4));
     } else {
-      NVD_TRY(launch_mlp_fp32(ctx, *m, d_in, NVD_F32, rows, d_soft, hard_host ? d_hard : nullptr, 4));
+      NVD_TRY(launch_mlp_fp32(ctx, *m, set[k].in, NVD_F32, rows, set[k].soft, set[k].hard, 4));
     }
-    if (soft_host) NVD_CUDA(cudaMemcpyAsync(soft_host + r0 * n_out, d_soft, static_cast<size_t>(rows) * n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hard_host) NVD_CUDA(cudaMemcpyAsync(hard_host + r0, d_hard, static_cast<size_t>(rows) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    NVD_CUDA(cudaStreamSynchronize(ctx->stream));  // d_* are reused by the next chunk
+    NVD_CUDA(cudaEventRecord(ev_done[k], ctx->stream));
+    if (c >= 1) NVD_TRY(copy_out(c - 1));        // after the launch of chunk c: a blocking pageable copy leaves the GPU busy
   }
+  NVD_TRY(copy_out(n_chunks - 1));
+  NVD_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  NVD_CUDA(cudaStreamSynchronize(ctx->copy_in));
   return nvd_sync(ctx);
 }
 
@@ -578,6 +665,8 @@ int nvd_lstm_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, const 
   CTX_GUARD(ctx);
   NVD_REQUIRE(model >= 0 && model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[model].live, "bad LSTM handle %d", model);
   NVD_REQUIRE(T_enc >= 1 && T_dec >= 1 && B >= 0 && (B == 0 || y), "bad shape / null input");
+  NVD_REQUIRE(known_dtype(y_dtype), "unknown y_dtype %d", y_dtype);
+  y_dtype = storage_dtype(y_dtype);
   if (fast_math == 2)   // bf16 tensor-core recurrence (tcgen05, h in tensor memory)
     return launch_lstm_tc(ctx, ctx->lstms[model], y, y_dtype, dec_in, T_enc, T_dec, B, logits_out, hard_packed);
   return launch_lstm(ctx, ctx->lstms[model], y, y_dtype, dec_in, T_enc, T_dec, B, fast_math, logits_out, hard_packed);
@@ -688,6 +777,196 @@ int nvd_mc_run(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host,
       const int64_t n = static_cast<int64_t>(std::min<uint64_t>(b.chunk, cfg->frames - done));
       NVD_TRY(staged_chunk(ctx, cfg, m, b, sigma, idx, cfg->frame0 + done, n, false, counters_dev + 4 * i, ctx->stage_timing));
     }
+  }
+  return NVD_OK;
+}
+
+// ---- per-bit predictor and recurrent decoder: Monte-Carlo steps over long frames ---------------------------------
+static uint32_t state_prefix(int state, int n_bits) {
+  // extract_state_bits is MSB-first in time (src/fnn_viterbi_bitwise.py:134-137): time t carries bit (n-1-t) of the number
+  uint32_t v = 0;
+  for (int t = 0; t < n_bits; ++t) v |= ((static_cast<uint32_t>(state) >> (n_bits - 1 - t)) & 1u) << t;
+  return v;
+}
+
+struct StageTimer {
+  nvd_ctx* ctx; bool on; int i = 0;
+  void mark() { if (on) cudaEventRecord(ctx->stage_ev[i++], ctx->stream); }
+  void finish() {
+    if (!on) return;
+    cudaEventSynchronize(ctx->stage_ev[i - 1]);
+    for (int k = 0; k + 1 < i && k < 5; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[k], ctx->stage_ev[k + 1]); ctx->stage_ms[k] += ms; }
+  }
+};
+
+int nvd_prepend_state(nvd_ctx* ctx, const uint8_t* info_packed, int L, int state, int n_state_bits, int64_t B, uint8_t* out) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(L >= 1 && n_state_bits >= 0 && n_state_bits <= 8, "bad L / n_state_bits");
+  NVD_REQUIRE(B >= 0 && (B == 0 || (info_packed && out)), "bad B / null buffer");
+  return launch_prepend_bits(ctx, info_packed, L, state_prefix(state, n_state_bits), n_state_bits, B, out);
+}
+
+int nvd_count_bit_errors(nvd_ctx* ctx, const uint8_t* pred, const uint8_t* info_packed, int info_stride_bytes, int bit_position,
+                         int64_t B, uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(B >= 0 && counters_dev && (B == 0 || (pred && info_packed)), "bad B / null buffer");
+  NVD_REQUIRE(info_stride_bytes >= 1 && bit_position >= 0 && bit_position < 8 * info_stride_bytes, "bit_position outside the row");
+  return launch_count_bit(ctx, pred, info_packed, info_stride_bytes, bit_position, B, counters_dev);
+}
+
+int nvd_count_row_errors(nvd_ctx* ctx, const uint8_t* pred_packed, int pred_stride_bytes, const uint8_t* info_packed,
+                         int info_stride_bytes, int L, int64_t B, uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(B >= 0 && counters_dev && (B == 0 || (pred_packed && info_packed)), "bad B / null buffer");
+  NVD_REQUIRE(L >= 1 && L <= 8 * pred_stride_bytes && L <= 8 * info_stride_bytes, "L=%d does not fit the row strides", L);
+  return launch_count_rows(ctx, pred_packed, pred_stride_bytes, info_packed, info_stride_bytes, L, B, counters_dev);
+}
+
+int nvd_mc_run_bitwise(nvd_ctx* ctx, const nvd_mc_bitwise_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host,
+                       int n_snr, uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(cfg && cfg->struct_bytes == static_cast<int32_t>(sizeof(nvd_mc_bitwise_config)), "bad nvd_mc_bitwise_config (struct_bytes)");
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, cfg->model, &m));
+  NVD_REQUIRE(snr_db_host && counters_dev && n_snr >= 1, "null argument / n_snr < 1");
+  NVD_REQUIRE(cfg->L >= 1 && cfg->L <= 65536 && cfg->n_state_bits >= 0 && cfg->n_state_bits <= 8, "bad L / n_state_bits");
+  NVD_REQUIRE(cfg->bit_position >= 0 && cfg->bit_position < cfg->L, "bit_position %d outside the frame", cfg->bit_position);
+  NVD_REQUIRE(cfg->code == NVD_CODE_57_REF || cfg->code == NVD_CODE_133171 || cfg->code == NVD_CODE_57_CAUSAL, "unknown code %d", cfg->code);
+  const int Lt = cfg->L + cfg->n_state_bits, n = 2 * Lt;
+  NVD_REQUIRE(m->dims[0] == n, "model input width %d != 2 (L + n_state_bits) = %d", m->dims[0], n);
+  NVD_REQUIRE(m->dims[m->n_layers] == 2, "the per-bit predictor has two outputs (got %d)", m->dims[m->n_layers]);
+  const bool tc = cfg->precision == NVD_PREC_BF16_TC;
+  NVD_REQUIRE(tc || cfg->precision == NVD_PREC_FP32, "unknown precision %d", cfg->precision);
+  if (tc && !m->ks_image) { set_error("model %d has no K-streamed tensor-core image", cfg->model); return NVD_ERR_UNSUPPORTED; }
+  NVD_REQUIRE(cfg->mode == NVD_MC_STAGED || (cfg->mode == NVD_MC_FUSED && tc), "fused mode runs on the BF16 tensor-core path");
+  if (cfg->frames == 0) return NVD_OK;
+  const uint32_t prefix = state_prefix(cfg->state, cfg->n_state_bits);
+  if (cfg->mode == NVD_MC_FUSED) {
+    for (int i = 0; i < n_snr; ++i)
+      NVD_TRY(launch_mlp_kstream_fused(ctx, *m, cfg->code, cfg->L, prefix, cfg->n_state_bits, cfg->bit_position, cfg->trunc,
+                                       sigma_of_db(snr_db_host[i]), snr_idx_host ? snr_idx_host[i] : i, cfg->frame0, cfg->frames,
+                                       counters_dev + 4 * i));
+    return NVD_OK;
+  }
+  const int64_t chunk = std::min<int64_t>(static_cast<int64_t>(cfg->frames), int64_t(1) << 18);
+  const size_t S_in = (cfg->L + 7) / 8, S_pre = (Lt + 7) / 8, S_c = (n + 7) / 8, ys = static_cast<size_t>(n) * (tc ? 2 : 4);
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_pre = al(chunk * S_in), o_c = o_pre + al(chunk * S_pre), o_y = o_c + al(chunk * S_c), o_p = o_y + al(chunk * ys);
+  NVD_TRY(ensure_mc_buf(ctx, o_p + al(chunk)));
+  char* base = static_cast<char*>(ctx->mc_buf);
+  uint8_t* d_info = reinterpret_cast<uint8_t*>(base);
+  uint8_t* d_pre = cfg->n_state_bits ? reinterpret_cast<uint8_t*>(base + o_pre) : d_info;
+  uint8_t* d_coded = reinterpret_cast<uint8_t*>(base + o_c);
+  void* d_y = base + o_y;
+  uint8_t* d_pred = reinterpret_cast<uint8_t*>(base + o_p);
+  const int y_dtype = tc ? (cfg->trunc ? NVD_BF16_TRUNC : NVD_BF16) : (cfg->trunc ? NVD_I32_TRUNC : NVD_F32);
+  for (int i = 0; i < 5; ++i) ctx->stage_ms[i] = 0;
+  for (int i = 0; i < n_snr; ++i) {
+    const int idx = snr_idx_host ? snr_idx_host[i] : i;
+    const float sigma = sigma_of_db(snr_db_host[i]);
+    for (uint64_t done = 0; done < cfg->frames; done += chunk) {
+      const int64_t nfr = static_cast<int64_t>(std::min<uint64_t>(chunk, cfg->frames - done));
+      const uint64_t f0 = cfg->frame0 + done;
+      StageTimer t{ctx, ctx->stage_timing};
+      t.mark();
+      NVD_TRY(launch_source(ctx, cfg->L, f0, nfr, d_info));
+      if (cfg->n_state_bits) NVD_TRY(launch_prepend_bits(ctx, d_info, cfg->L, prefix, cfg->n_state_bits, nfr, d_pre));
+      t.mark();
+      NVD_TRY(launch_encode(ctx, cfg->code, d_pre, Lt, nfr, d_coded));
+      t.mark();
+      NVD_TRY(launch_channel(ctx, d_coded, n, nfr, sigma, idx, f0, y_dtype, d_y));
+      t.mark();
+      if (tc) NVD_TRY(launch_mlp_kstream(ctx, *m, static_cast<const __nv_bfloat16*>(d_y), n, nfr, nullptr, d_pred, 1));
+      else NVD_TRY(launch_mlp_fp32(ctx, *m, d_y, storage_dtype(y_dtype), nfr, nullptr, d_pred, 1));
+      t.mark();
+      NVD_TRY(launch_count_bit(ctx, d_pred, d_info, static_cast<int>(S_in), cfg->bit_position, nfr, counters_dev + 4 * i));
+      t.mark();
+      t.finish();
+    }
+  }
+  return NVD_OK;
+}
+
+int nvd_mc_run_lstm(nvd_ctx* ctx, const nvd_mc_lstm_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host, int n_snr,
+                    uint64_t* counters_dev) {
+  CTX_GUARD(ctx);
+  NVD_REQUIRE(cfg && cfg->struct_bytes == static_cast<int32_t>(sizeof(nvd_mc_lstm_config)), "bad nvd_mc_lstm_config (struct_bytes)");
+  NVD_REQUIRE(cfg->model >= 0 && cfg->model < static_cast<int>(ctx->lstms.size()) && ctx->lstms[cfg->model].live, "bad LSTM handle %d", cfg->model);
+  NVD_REQUIRE(snr_db_host && counters_dev && n_snr >= 1, "null argument / n_snr < 1");
+  NVD_REQUIRE(cfg->L >= 1 && cfg->L <= 4096, "L=%d out of range", cfg->L);
+  NVD_REQUIRE(cfg->code == NVD_CODE_57_REF || cfg->code == NVD_CODE_133171 || cfg->code == NVD_CODE_57_CAUSAL, "unknown code %d", cfg->code);
+  NVD_REQUIRE(cfg->fast_math >= 0 && cfg->fast_math <= 2, "fast_math must be 0, 1 or 2");
+  if (cfg->frames == 0) return NVD_OK;
+  const LstmModel& m = ctx->lstms[cfg->model];
+  const int L = cfg->L, T = 2 * L;
+  const int64_t chunk = std::min<int64_t>(static_cast<int64_t>(cfg->frames), int64_t(1) << 20);
+  const size_t S_in = (L + 7) / 8, S_c = (T + 7) / 8, S_h = (T + 7) / 8;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_c = al(chunk * S_in), o_y = o_c + al(chunk * S_c), o_d = o_y + al(chunk * T * 4);
+  const size_t o_h = o_d + (cfg->teacher_forced ? al(chunk * T * 4) : 0);
+  NVD_TRY(ensure_mc_buf(ctx, o_h + al(chunk * S_h)));
+  char* base = static_cast<char*>(ctx->mc_buf);
+  uint8_t* d_info = reinterpret_cast<uint8_t*>(base);
+  uint8_t* d_coded = reinterpret_cast<uint8_t*>(base + o_c);
+  void* d_y = base + o_y;
+  float* d_dec = cfg->teacher_forced ? reinterpret_cast<float*>(base + o_d) : nullptr;
+  uint8_t* d_hard = reinterpret_cast<uint8_t*>(base + o_h);
+  const int y_dtype = cfg->trunc ? NVD_I32_TRUNC : NVD_F32;
+  for (int i = 0; i < 5; ++i) ctx->stage_ms[i] = 0;
+  for (int i = 0; i < n_snr; ++i) {
+    const int idx = snr_idx_host ? snr_idx_host[i] : i;
+    const float sigma = sigma_of_db(snr_db_host[i]);
+    for (uint64_t done = 0; done < cfg->frames; done += chunk) {
+      const int64_t nfr = static_cast<int64_t>(std::min<uint64_t>(chunk, cfg->frames - done));
+      const uint64_t f0 = cfg->frame0 + done;
+      StageTimer t{ctx, ctx->stage_timing};
+      t.mark();
+      NVD_TRY(launch_source(ctx, L, f0, nfr, d_info));
+      t.mark();
+      NVD_TRY(launch_encode(ctx, cfg->code, d_info, L, nfr, d_coded));
+      t.mark();
+      NVD_TRY(launch_channel(ctx, d_coded, T, nfr, sigma, idx, f0, y_dtype, d_y));
+      if (d_dec) NVD_TRY(launch_teacher_inputs(ctx, d_info, static_cast<int>(S_in), L, T, nfr, d_dec));
+      t.mark();
+      if (cfg->fast_math == 2) NVD_TRY(launch_lstm_tc(ctx, m, d_y, y_dtype, d_dec, T, T, nfr, nullptr, d_hard));
+      else NVD_TRY(launch_lstm(ctx, m, d_y, y_dtype, d_dec, T, T, nfr, cfg->fast_math, nullptr, d_hard));
+      t.mark();
+      NVD_TRY(launch_count_rows(ctx, d_hard, static_cast<int>(S_h), d_info, static_cast<int>(S_in), L, nfr, counters_dev + 4 * i));
+      t.mark();
+      t.finish();
+    }
+  }
+  return NVD_OK;
+}
+
+int nvd_mc_sweep(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_host, const int32_t* snr_idx_host, int n_snr,
+                 uint64_t min_frame_errors, uint64_t max_frames, uint64_t chunk_frames, uint64_t* counters_host) {
+  CTX_GUARD(ctx);
+  MlpModel* m;
+  NVD_TRY(validate_mc(ctx, cfg, &m));
+  NVD_REQUIRE(snr_db_host && counters_host && n_snr >= 1, "null argument / n_snr < 1");
+  NVD_REQUIRE(chunk_frames >= 1 && max_frames >= 1, "chunk_frames and max_frames must be positive");
+  const uint64_t world = static_cast<uint64_t>(ctx->comm_world), rank = static_cast<uint64_t>(ctx->comm_rank);
+  // per-chunk counters on the device (summed over ranks in place), totals on the host
+  uint64_t* d_chunk = ctx->counters_scratch;
+  for (int i = 0; i < n_snr; ++i) {
+    uint64_t total[4] = {0, 0, 0, 0};
+    const int32_t idx = snr_idx_host ? snr_idx_host[i] : i;
+    for (uint64_t done = 0; done < max_frames && total[1] < min_frame_errors;) {
+      const uint64_t n = std::min(chunk_frames, max_frames - done);
+      const uint64_t lo = n * rank / world, hi = n * (rank + 1) / world;     // this rank's share of the chunk
+      nvd_mc_config c = *cfg;
+      c.frame0 = cfg->frame0 + done + lo;
+      c.frames = hi - lo;
+      NVD_CUDA(cudaMemsetAsync(d_chunk, 0, 4 * sizeof(uint64_t), ctx->stream));
+      NVD_TRY(nvd_mc_run(ctx, &c, snr_db_host + i, &idx, 1, d_chunk));
+      NVD_TRY(comm_allreduce_u64(ctx, d_chunk, 4));
+      NVD_CUDA(queue_tail_copy(ctx));
+      NVD_TRY(finish_tail(ctx));
+      for (int k = 0; k < 4; ++k) total[k] += ctx->counters_pinned[k];
+      done += n;
+    }
+    for (int k = 0; k < 4; ++k) counters_host[4 * i + k] = total[k];
   }
   return NVD_OK;
 }

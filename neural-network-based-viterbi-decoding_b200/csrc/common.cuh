@@ -61,6 +61,10 @@ struct MlpModel {
   // layer-per-launch tensor-core path for wide layers (k_mlp_wide_tc.cu): one bf16 image per layer
   bool wide = false;
   void* wide_image[kMaxLayers] = {nullptr};
+  // K-streamed tensor-core path for tall-and-skinny two-layer nets (k_mlp_kstream.cu): bf16 W1 image + fp32 tail
+  void* ks_image = nullptr;
+  float* ks_l2 = nullptr;
+  int ks_Kpad = 0, ks_N1pad = 0;
   float* tc_bias_out = nullptr;  // reserved
   float tc_out_offset = 0.0f;    // power of two added to the output accumulators (positive-key argmax)
 };
@@ -104,6 +108,9 @@ struct nvd_ctx {
   uint32_t* done_flags = nullptr;        // mapped pinned: slice s of the decisions is complete in device memory
   uint32_t* done_flags_dev = nullptr;    // ... its device-side address
   static constexpr int kMaxSlices = 1024;
+  // multi-GPU exchange step: NCCL communicator of this context's rank (comm.cu); null = single GPU
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   // staged-pipeline stage timing
   cudaEvent_t stage_ev[6] = {nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -113,6 +120,10 @@ struct nvd_ctx {
 namespace nvd {
 
 int ensure_scratch(nvd_ctx* ctx, size_t bytes);
+
+// comm.cu: in-place sum of n uint64 device values over the context's communicator, on ctx->stream (no-op without one)
+int comm_allreduce_u64(nvd_ctx* ctx, uint64_t* values_dev, size_t n);
+void comm_release(nvd_ctx* ctx);
 
 // ---- kernel launchers (each validates nothing; the API layer does) -----------------------
 int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed);
@@ -132,6 +143,25 @@ int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* co
 size_t wide_tc_scratch_bytes(const MlpModel& m, int64_t rows);
 int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src_dtype, int64_t src_len, int64_t row_stride,
                        int64_t B, void* scratch, float* soft_out, void* hard_out, int hard_bytes);
+
+// K-streamed tensor-core path (k_mlp_kstream.cu): [K, N1 <= 64, n_out <= 8] nets such as the bitwise 1036-30-2
+bool kstream_supported(const MlpModel& m);
+int kstream_build_image(MlpModel& m, const float* const* W_host, const float* const* b_host);
+// staged: bf16 rows [B, K] at `row_stride` elements -> soft [B, n_out] fp32 / hard class index
+int launch_mlp_kstream(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y, int64_t row_stride, int64_t B, float* soft_out,
+                       void* hard_out, int hard_bytes);
+// fused Monte-Carlo: frames generated on chip (prefix ++ Philox info bits -> encoder -> channel), decision compared
+// with info bit `bit_position`, counters accumulated
+int launch_mlp_kstream_fused(nvd_ctx* ctx, const MlpModel& m, int code, int L, uint32_t prefix_bits, int n_prefix, int bit_position,
+                             int trunc, float sigma, int snr_idx, uint64_t frame0, uint64_t frames, uint64_t* counters);
+
+// K0 helpers / K5 variants for long frames
+int launch_prepend_bits(nvd_ctx* ctx, const uint8_t* info, int L, uint32_t prefix_bits, int n_prefix, int64_t B, uint8_t* out);
+int launch_count_bit(nvd_ctx* ctx, const uint8_t* pred, const uint8_t* info, int info_stride, int bit_position, int64_t B,
+                     uint64_t* counters);
+int launch_count_rows(nvd_ctx* ctx, const uint8_t* pred, int pred_stride, const uint8_t* label, int label_stride, int L, int64_t B,
+                      uint64_t* counters);
+int launch_teacher_inputs(nvd_ctx* ctx, const uint8_t* info, int info_stride, int L, int T_dec, int64_t B, float* dec_in);
 
 // tensor-core recurrence (k_lstm_tc.cu)
 bool lstm_tc_supported(int H);

@@ -22,11 +22,14 @@ template <>
 struct OutT<NVD_BF16> { using type = __nv_bfloat16; };
 template <>
 struct OutT<NVD_I32_TRUNC> { using type = int32_t; };
+template <>
+struct OutT<NVD_BF16_TRUNC> { using type = __nv_bfloat16; };
 
 template <int kDtype>
 __device__ __forceinline__ typename OutT<kDtype>::type cast_out(float v) {
   if constexpr (kDtype == NVD_F32) return v;
   else if constexpr (kDtype == NVD_BF16) return __float2bfloat16_rn(v);
+  else if constexpr (kDtype == NVD_BF16_TRUNC) return __float2bfloat16_rn(truncf(v));   // the same integer, exact in bf16
   else return static_cast<int32_t>(v);  // truncation toward zero, as a numpy int32 row stores it
 }
 
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const
 #pragma unroll
     for (int k = 0; k < 6; k += 2) {
       if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + k)[0] = __floats2bfloat162_rn(v[k], v[k + 1]);
+      else if constexpr (kDtype == NVD_BF16_TRUNC) reinterpret_cast<__nv_bfloat162*>(row + k)[0] = __floats2bfloat162_rn(truncf(v[k]), truncf(v[k + 1]));
       else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + k)[0] = make_float2(v[k], v[k + 1]);
       else reinterpret_cast<int2*>(row + k)[0] = make_int2(cast_out<kDtype>(v[k]), cast_out<kDtype>(v[k + 1]));
     }
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk,
     const float a = fmaf(sigma, z[j], ((bits >> j) & 1u) ? 1.0f : -1.0f);
     const float b = fmaf(sigma, z[j + 1], ((bits >> (j + 1)) & 1u) ? 1.0f : -1.0f);
     if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(a, b);
+    else if constexpr (kDtype == NVD_BF16_TRUNC) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(truncf(a), truncf(b));
     else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + j)[0] = make_float2(a, b);
     else reinterpret_cast<int2*>(row + j)[0] = make_int2(cast_out<kDtype>(a), cast_out<kDtype>(b));
   }
@@ -127,7 +132,7 @@ int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float s
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
   const uint32_t sw = noise_stream_word(snr_idx);
   const PhiloxKeys rk = make_philox_keys(ctx->seed);
-  if (n <= 16 && (n & 1) == 0) {
+  if (n <= 16 && (n & 1) == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0) {   // the frame kernel stores 16-byte vectors
     const unsigned fgrid = static_cast<unsigned>((B + 255) / 256);
 #define NVD_LAUNCH_FRAME(DT, CT)                                                                                          \
   do {                                                                                                                    \
@@ -138,6 +143,7 @@ int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float s
       case NVD_F32: NVD_LAUNCH_FRAME(NVD_F32, float); break;
       case NVD_BF16: NVD_LAUNCH_FRAME(NVD_BF16, __nv_bfloat16); break;
       case NVD_I32_TRUNC: NVD_LAUNCH_FRAME(NVD_I32_TRUNC, int32_t); break;
+      case NVD_BF16_TRUNC: NVD_LAUNCH_FRAME(NVD_BF16_TRUNC, __nv_bfloat16); break;
       default:
         set_error("nvd_channel: unknown out_dtype %d", out_dtype);
         return NVD_ERR_INVALID;
@@ -157,6 +163,7 @@ int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float s
     case NVD_F32: NVD_LAUNCH_CHANNEL(NVD_F32, float); break;
     case NVD_BF16: NVD_LAUNCH_CHANNEL(NVD_BF16, __nv_bfloat16); break;
     case NVD_I32_TRUNC: NVD_LAUNCH_CHANNEL(NVD_I32_TRUNC, int32_t); break;
+    case NVD_BF16_TRUNC: NVD_LAUNCH_CHANNEL(NVD_BF16_TRUNC, __nv_bfloat16); break;
     default:
       set_error("nvd_channel: unknown out_dtype %d", out_dtype);
       return NVD_ERR_INVALID;

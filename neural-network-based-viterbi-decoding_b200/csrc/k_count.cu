@@ -99,7 +99,60 @@ __global__ void __launch_bounds__(256) count_generic_kernel(const uint8_t* __res
   block_accumulate(be, fe, counters, add_frames, add_bits);
 }
 
+// decision byte (0 / 1) against ONE bit of a packed info row: the per-bit predictor's test
+// (/root/reference/src/fnn_viterbi_bitwise.py:456-457 label, :504-509 decision and error rate)
+__global__ void __launch_bounds__(256) count_bit_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ info,
+                                                        int info_stride, int bit_position, int64_t B, uint64_t* counters) {
+  uint32_t e = 0;
+  for (int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; f < B; f += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t lab = (static_cast<uint32_t>(__ldg(info + f * info_stride + (bit_position >> 3))) >> (bit_position & 7)) & 1u;
+    e += (static_cast<uint32_t>(__ldg(pred + f)) ^ lab) & 1u;
+  }
+  block_accumulate(e, e, counters, static_cast<uint64_t>(B), static_cast<uint64_t>(B));
+}
+
+// packed rows with different strides (the recurrent decoder writes T_dec decision bits per frame, the label row holds
+// the L info bits; only the first L are scored, /root/reference/src/rnn_viterbi.py:477-491)
+__global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t* __restrict__ pred, int pred_stride,
+                                                         const uint8_t* __restrict__ label, int label_stride, int L, int64_t B,
+                                                         uint64_t* counters) {
+  uint32_t be = 0, fe = 0;
+  const int S = (L + 7) >> 3;
+  for (int64_t f = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; f < B; f += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint8_t* p = pred + f * pred_stride;
+    const uint8_t* l = label + f * label_stride;
+    uint32_t any = 0;
+    for (int b = 0; b < S; ++b) {
+      uint32_t x = static_cast<uint32_t>(p[b] ^ l[b]);
+      const int valid = L - 8 * b;
+      if (valid < 8) x &= (1u << valid) - 1u;
+      be += __popc(x);
+      any |= x;
+    }
+    fe += any ? 1u : 0u;
+  }
+  block_accumulate(be, fe, counters, static_cast<uint64_t>(B), static_cast<uint64_t>(B) * static_cast<uint64_t>(L));
+}
+
 }  // namespace
+
+int launch_count_bit(nvd_ctx* ctx, const uint8_t* pred, const uint8_t* info, int info_stride, int bit_position, int64_t B,
+                     uint64_t* counters) {
+  if (B == 0) return NVD_OK;
+  const int grid = static_cast<int>(std::min<int64_t>((B + 255) / 256, ctx->sm_count * 8));
+  count_bit_kernel<<<grid, 256, 0, ctx->stream>>>(pred, info, info_stride, bit_position, B, counters);
+  NVD_CHECK_LAUNCH();
+  return NVD_OK;
+}
+
+int launch_count_rows(nvd_ctx* ctx, const uint8_t* pred, int pred_stride, const uint8_t* label, int label_stride, int L, int64_t B,
+                      uint64_t* counters) {
+  if (B == 0) return NVD_OK;
+  const int grid = static_cast<int>(std::min<int64_t>((B + 255) / 256, ctx->sm_count * 8));
+  count_rows_kernel<<<grid, 256, 0, ctx->stream>>>(pred, pred_stride, label, label_stride, L, B, counters);
+  NVD_CHECK_LAUNCH();
+  return NVD_OK;
+}
 
 int launch_count(nvd_ctx* ctx, const void* pred, const void* label, int stride, int L, int64_t B, int flags,
                  uint64_t* counters) {

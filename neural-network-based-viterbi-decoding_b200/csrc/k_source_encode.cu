@@ -106,6 +106,58 @@ int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info
   return NVD_OK;
 }
 
+// n_prefix (<= 8) time-packed bits in front of every frame: the six start-state bits that encode_133171_with_state
+// prepends (/root/reference/src/fnn_viterbi_bitwise.py:162-163).  One output byte per thread.
+__global__ void __launch_bounds__(256) prepend_bits_kernel(const uint8_t* __restrict__ in, int L, int S_in, int S_out,
+                                                           uint32_t prefix_bits, int n_prefix, int64_t B, uint8_t* __restrict__ out) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= B * S_out) return;
+  const int64_t f = t / S_out;
+  const int b = static_cast<int>(t - f * S_out);
+  const uint8_t* row = in + f * S_in;
+  auto info_byte = [&](int i) -> uint32_t {       // masked to the L valid bits
+    if (i < 0 || i >= S_in) return 0u;
+    uint32_t v = row[i];
+    const int valid = L - 8 * i;
+    return valid < 8 ? (v & ((1u << valid) - 1u)) : v;
+  };
+  uint32_t v;
+  if (b == 0) v = prefix_bits | (info_byte(0) << n_prefix);
+  else v = ((info_byte(b - 1) | (info_byte(b) << 8)) >> (8 - n_prefix));
+  out[t] = static_cast<uint8_t>(v);
+}
+
+int launch_prepend_bits(nvd_ctx* ctx, const uint8_t* info, int L, uint32_t prefix_bits, int n_prefix, int64_t B, uint8_t* out) {
+  if (B == 0) return NVD_OK;
+  const int S_in = (L + 7) / 8, S_out = (L + n_prefix + 7) / 8;
+  const int64_t threads = B * S_out;
+  prepend_bits_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(info, L, S_in, S_out, prefix_bits, n_prefix, B, out);
+  NVD_CHECK_LAUNCH();
+  return NVD_OK;
+}
+
+// teacher-forced decoder inputs of the recurrent decoder, [B, T_dec] fp32: EOS (1.0), the L info bits as -1/+1, zeros
+// (prepare_batch, /root/reference/src/rnn_viterbi.py:362-371)
+__global__ void __launch_bounds__(256) teacher_inputs_kernel(const uint8_t* __restrict__ info, int info_stride, int L, int T_dec,
+                                                             int64_t B, float* __restrict__ dec_in) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= B * T_dec) return;
+  const int64_t f = t / T_dec;
+  const int j = static_cast<int>(t - f * T_dec);
+  float v = 0.0f;
+  if (j == 0) v = 1.0f;
+  else if (j <= L) v = ((info[f * info_stride + ((j - 1) >> 3)] >> ((j - 1) & 7)) & 1u) ? 1.0f : -1.0f;
+  dec_in[t] = v;
+}
+
+int launch_teacher_inputs(nvd_ctx* ctx, const uint8_t* info, int info_stride, int L, int T_dec, int64_t B, float* dec_in) {
+  if (B == 0) return NVD_OK;
+  const int64_t threads = B * T_dec;
+  teacher_inputs_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(info, info_stride, L, T_dec, B, dec_in);
+  NVD_CHECK_LAUNCH();
+  return NVD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 vector path: S_out == 2*S_in, 16 input bytes per thread.
 // ---------------------------------------------------------------------------------------------

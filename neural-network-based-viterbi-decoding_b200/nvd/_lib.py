@@ -14,14 +14,15 @@ HEADER_PATH = os.path.join(ROOT_DIR, "include", "nvd.h")
 # enums of include/nvd.h
 OK = 0
 CODE_57_REF, CODE_133171, CODE_57_CAUSAL = 0, 1, 2
-F32, BF16, I32_TRUNC = 0, 1, 2
+F32, BF16, I32_TRUNC, BF16_TRUNC = 0, 1, 2, 3
 ACT_IDENTITY, ACT_TANH, ACT_RELU = 0, 1, 2
 PREC_FP32, PREC_BF16_TC = 0, 1
 MC_STAGED, MC_FUSED = 0, 1
 COUNT_PRED_IS_MSB_CLASS = 1
+COMM_ID_BYTES = 128
 
 CODES = {"57": CODE_57_REF, "57_ref": CODE_57_REF, "133171": CODE_133171, "57_causal": CODE_57_CAUSAL}
-DTYPES = {"f32": F32, "bf16": BF16, "i32_trunc": I32_TRUNC}
+DTYPES = {"f32": F32, "bf16": BF16, "i32_trunc": I32_TRUNC, "bf16_trunc": BF16_TRUNC}
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16_TC}
 
 
@@ -34,6 +35,18 @@ class NvdError(RuntimeError):
 class McConfig(C.Structure):
     _fields_ = [("struct_bytes", C.c_int32), ("model", C.c_int32), ("code", C.c_int32), ("L", C.c_int32),
                 ("precision", C.c_int32), ("mode", C.c_int32), ("y_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("frame0", C.c_uint64), ("frames", C.c_uint64)]
+
+
+class McBitwiseConfig(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("model", C.c_int32), ("code", C.c_int32), ("L", C.c_int32),
+                ("n_state_bits", C.c_int32), ("state", C.c_int32), ("bit_position", C.c_int32), ("precision", C.c_int32),
+                ("mode", C.c_int32), ("trunc", C.c_int32), ("frame0", C.c_uint64), ("frames", C.c_uint64)]
+
+
+class McLstmConfig(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("model", C.c_int32), ("code", C.c_int32), ("L", C.c_int32),
+                ("fast_math", C.c_int32), ("teacher_forced", C.c_int32), ("trunc", C.c_int32), ("reserved", C.c_int32),
                 ("frame0", C.c_uint64), ("frames", C.c_uint64)]
 
 
@@ -76,6 +89,17 @@ _PROTOS = {
     "nvd_mc_run_host": ([_vp, C.POINTER(McConfig), _f, _i, _vp, _vp, _vp], _i),
     "nvd_mc_stage_ms": ([_vp, C.POINTER(_f)], _i),
     "nvd_mc_set_stage_timing": ([_vp, _i], _i),
+    "nvd_mc_run_bitwise": ([_vp, C.POINTER(McBitwiseConfig), C.POINTER(_f), C.POINTER(C.c_int32), _i, _vp], _i),
+    "nvd_mc_run_lstm": ([_vp, C.POINTER(McLstmConfig), C.POINTER(_f), C.POINTER(C.c_int32), _i, _vp], _i),
+    "nvd_count_bit_errors": ([_vp, _vp, _vp, _i, _i, _i64, _vp], _i),
+    "nvd_count_row_errors": ([_vp, _vp, _i, _vp, _i, _i, _i64, _vp], _i),
+    "nvd_prepend_state": ([_vp, _vp, _i, _i, _i, _i64, _vp], _i),
+    "nvd_comm_unique_id": ([_vp], _i),
+    "nvd_comm_init": ([_vp, _i, _i, _vp], _i),
+    "nvd_comm_destroy": ([_vp], _i),
+    "nvd_comm_info": ([_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)], _i),
+    "nvd_comm_allreduce_u64": ([_vp, _vp, C.c_size_t], _i),
+    "nvd_mc_sweep": ([_vp, C.POINTER(McConfig), C.POINTER(_f), C.POINTER(C.c_int32), _i, _u64, _u64, _u64, _vp], _i),
     "nvd_debug_tc_timing": ([_vp, _i, _u64, _vp], _i),
     "nvd_debug_umma_probe_ts": ([_vp, _i, _i, _i, _vp, _vp, _vp], _i),
     "nvd_debug_umma_probe": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),

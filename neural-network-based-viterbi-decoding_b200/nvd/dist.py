@@ -62,6 +62,22 @@ def all_reduce_max(value: float) -> float:
     return float(t.item())
 
 
+def broadcast_bytes(data: bytes | None, nbytes: int, src: int = 0) -> bytes:
+    """Ship a small byte string from rank `src` to every rank (the NCCL unique id of nvd_comm_init)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return bytes(data)
+    t = torch.zeros(nbytes, dtype=torch.uint8)
+    if dist.get_rank() == src:
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
 def barrier():
     import torch.distributed as dist
 

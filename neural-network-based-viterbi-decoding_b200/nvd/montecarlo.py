@@ -90,6 +90,7 @@ class Simulator:
         self.seed = seed
         self._bufs = []
         self._n_out = {}
+        self.rank, self.world = 0, 1
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
@@ -100,6 +101,7 @@ class Simulator:
                 except NvdError:
                     pass
             self._bufs = []
+            self.lib.nvd_comm_destroy(self.ctx)
             self.lib.nvd_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -126,6 +128,33 @@ class Simulator:
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         check(self.lib.nvd_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
         return dict(sm_count=sm.value, cc=(ma.value, mi.value), total_mem=mem.value)
+
+    # -- multi-GPU exchange step (include/nvd.h: nvd_comm_*) -------------------------------------------
+    def comm_init(self, rank: int, world: int, broadcast=None):
+        """Create this context's NCCL communicator.  `broadcast(bytes_or_None, nbytes) -> bytes` ships rank 0's
+        unique id to the other ranks (default: torch.distributed, nvd.dist.broadcast_bytes)."""
+        if world <= 1:
+            return
+        if broadcast is None:
+            from . import dist
+            broadcast = dist.broadcast_bytes
+        raw = None
+        if rank == 0:
+            buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+            check(self.lib.nvd_comm_unique_id(buf))
+            raw = buf.raw
+        raw = broadcast(raw, _lib.COMM_ID_BYTES)
+        check(self.lib.nvd_comm_init(self.ctx, rank, world, C.create_string_buffer(raw, _lib.COMM_ID_BYTES)))
+        self.rank, self.world = rank, world
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.nvd_comm_info(self.ctx, C.byref(r), C.byref(w), C.byref(v)))
+        return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+    def allreduce_counters(self, counters: "DeviceBuffer", n_u64: int):
+        """In-place ncclAllReduce(sum) of n uint64 device values on the library's stream (asynchronous)."""
+        check(self.lib.nvd_comm_allreduce_u64(self.ctx, counters.ptr, n_u64))
 
     # -- memory / timing -------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> DeviceBuffer:
@@ -336,6 +365,85 @@ class Simulator:
                                        pred_host.ctypes.data if pred_host is not None else None, counters.ctypes.data))
         return counters
 
+    def run_bitwise_async(self, h, L, snr_db, frames, counters: DeviceBuffer, frame0=0, mode="fused", precision="bf16",
+                          code="133171", n_state_bits=6, state=0, bit_position=0, trunc=True, snr_idx=None):
+        """Enqueue the per-bit predictor's Monte-Carlo step (nvd_mc_run_bitwise): Philox info bits, start-state prefix,
+        encoder, channel (int32-truncated like the reference's data sets when `trunc`), 1036-30-2 forward, decision
+        against info bit `bit_position`; counters [n_snr, 4] accumulated on the device."""
+        snr_db = np.atleast_1d(np.asarray(snr_db, dtype=np.float32))
+        idx = np.arange(len(snr_db), dtype=np.int32) if snr_idx is None else np.asarray(snr_idx, dtype=np.int32)
+        cfg = _lib.McBitwiseConfig()
+        cfg.struct_bytes = C.sizeof(_lib.McBitwiseConfig)
+        cfg.model, cfg.code, cfg.L = h, _code(code), L
+        cfg.n_state_bits, cfg.state, cfg.bit_position = n_state_bits, state, bit_position
+        cfg.precision = _lib.PRECISIONS[precision]
+        cfg.mode = _lib.MC_FUSED if mode == "fused" else _lib.MC_STAGED
+        cfg.trunc = int(bool(trunc))
+        cfg.frame0, cfg.frames = int(frame0), int(frames)
+        check(self.lib.nvd_mc_run_bitwise(self.ctx, C.byref(cfg), snr_db.ctypes.data_as(C.POINTER(C.c_float)),
+                                          idx.ctypes.data_as(C.POINTER(C.c_int32)), len(snr_db), counters.ptr))
+
+    def run_bitwise(self, h, L, snr_db, frames, frame0=0, rank=0, world=1, **kw) -> np.ndarray:
+        """Synchronous form; with world > 1 this rank runs its shard and the library all-reduces the counters."""
+        snr_db = np.atleast_1d(np.asarray(snr_db, dtype=np.float32))
+        lo, n = shard_range(frame0, frames, rank, world)
+        counters = self.zeros(len(snr_db) * 32)
+        self.run_bitwise_async(h, L, snr_db, n, counters, lo, **kw)
+        if world > 1:
+            self.allreduce_counters(counters, 4 * len(snr_db))
+        out = counters.download(np.uint64, (len(snr_db), 4))
+        self.free(counters)
+        return out
+
+    def run_lstm_async(self, h, L, snr_db, frames, counters: DeviceBuffer, frame0=0, fast_math=2, teacher_forced=True,
+                       code="133171", trunc=True, snr_idx=None):
+        """Enqueue the recurrent decoder's Monte-Carlo step (nvd_mc_run_lstm): Philox info bits, encoder, channel,
+        LSTM seq2seq over 2L + 2L steps, decision bits of the first L decoder steps against the info bits."""
+        snr_db = np.atleast_1d(np.asarray(snr_db, dtype=np.float32))
+        idx = np.arange(len(snr_db), dtype=np.int32) if snr_idx is None else np.asarray(snr_idx, dtype=np.int32)
+        cfg = _lib.McLstmConfig()
+        cfg.struct_bytes = C.sizeof(_lib.McLstmConfig)
+        cfg.model, cfg.code, cfg.L = h, _code(code), L
+        cfg.fast_math, cfg.teacher_forced, cfg.trunc = int(fast_math), int(bool(teacher_forced)), int(bool(trunc))
+        cfg.frame0, cfg.frames = int(frame0), int(frames)
+        check(self.lib.nvd_mc_run_lstm(self.ctx, C.byref(cfg), snr_db.ctypes.data_as(C.POINTER(C.c_float)),
+                                       idx.ctypes.data_as(C.POINTER(C.c_int32)), len(snr_db), counters.ptr))
+
+    def run_lstm(self, h, L, snr_db, frames, frame0=0, rank=0, world=1, **kw) -> np.ndarray:
+        snr_db = np.atleast_1d(np.asarray(snr_db, dtype=np.float32))
+        lo, n = shard_range(frame0, frames, rank, world)
+        counters = self.zeros(len(snr_db) * 32)
+        self.run_lstm_async(h, L, snr_db, n, counters, lo, **kw)
+        if world > 1:
+            self.allreduce_counters(counters, 4 * len(snr_db))
+        out = counters.download(np.uint64, (len(snr_db), 4))
+        self.free(counters)
+        return out
+
+    def count_bit_errors(self, pred: np.ndarray, info_bits: np.ndarray, bit_position: int) -> np.ndarray:
+        """Decisions (0/1) [B] against bit `bit_position` of info rows {0,1} [B, L] on K5 -> counters uint64[4]."""
+        pred = np.ascontiguousarray(pred, dtype=np.uint8)
+        packed = np.packbits(np.asarray(info_bits, dtype=np.uint8) & 1, axis=1, bitorder="little")
+        d_p, d_i, c = self.to_device(pred), self.to_device(packed), self.zeros(32)
+        check(self.lib.nvd_count_bit_errors(self.ctx, d_p.ptr, d_i.ptr, packed.shape[1], bit_position, len(pred), c.ptr))
+        out = c.download(np.uint64, (4,))
+        for b in (d_p, d_i, c):
+            self.free(b)
+        return out
+
+    def count_row_errors(self, pred_bits: np.ndarray, info_bits: np.ndarray) -> np.ndarray:
+        """Decision rows {0,1} [B, >= L] against info rows {0,1} [B, L] on K5 (first L bits) -> counters uint64[4]."""
+        info_bits = np.asarray(info_bits, dtype=np.uint8) & 1
+        L = info_bits.shape[1]
+        pp = np.packbits(np.asarray(pred_bits, dtype=np.uint8) & 1, axis=1, bitorder="little")
+        ip = np.packbits(info_bits, axis=1, bitorder="little")
+        d_p, d_i, c = self.to_device(pp), self.to_device(ip), self.zeros(32)
+        check(self.lib.nvd_count_row_errors(self.ctx, d_p.ptr, pp.shape[1], d_i.ptr, ip.shape[1], L, len(pp), c.ptr))
+        out = c.download(np.uint64, (4,))
+        for b in (d_p, d_i, c):
+            self.free(b)
+        return out
+
     def stage_ms(self):
         ms = (C.c_float * 5)()
         check(self.lib.nvd_mc_stage_ms(self.ctx, ms))
@@ -347,8 +455,18 @@ class Simulator:
     def sweep(self, h, code, L, snr_db, min_frame_errors=100, max_frames=1 << 34, chunk_frames=1 << 26, mode="fused",
               precision="bf16", rank=0, world=1, all_reduce=None, frame0=0):
         """Deep-BER driver: per SNR point, add chunks of frames until >= min_frame_errors frame
-        errors (global, after the all-reduce) or max_frames.  Returns counters [n_snr, 4]."""
+        errors (global, after the all-reduce) or max_frames.  Returns counters [n_snr, 4].
+        Without an `all_reduce` callable this is ONE C-ABI call (nvd_mc_sweep): the library shards every chunk over
+        the ranks of its communicator (comm_init) and all-reduces the counters on its own stream."""
         snr_db = np.atleast_1d(np.asarray(snr_db, dtype=np.float32))
+        if all_reduce is None and (world == 1 or self.world == world):
+            cfg = self._mc_config(h, code, L, precision, mode, "bf16" if precision == "bf16" else "f32", frame0, 0)
+            idx = np.arange(len(snr_db), dtype=np.int32)
+            out = np.zeros((len(snr_db), 4), dtype=np.uint64)
+            check(self.lib.nvd_mc_sweep(self.ctx, C.byref(cfg), snr_db.ctypes.data_as(C.POINTER(C.c_float)),
+                                        idx.ctypes.data_as(C.POINTER(C.c_int32)), len(snr_db), int(min_frame_errors),
+                                        int(max_frames), int(chunk_frames), out.ctypes.data))
+            return out
         total = np.zeros((len(snr_db), 4), dtype=np.uint64)
         for i, db in enumerate(snr_db):
             done = 0

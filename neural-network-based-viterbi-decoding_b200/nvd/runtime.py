@@ -52,9 +52,67 @@ def precision() -> str:
     return _precision
 
 
+# ---- loaded-model cache ------------------------------------------------------------------------------------
+# The reference keeps its variables inside one tf.Session across calls; the drop-in functions receive plain
+# weight dicts on every call.  Loading a model (device allocations, image build, synchronous copies) per decode
+# call would dominate small batches, so handles are cached by the CONTENT of the parameters (a changed array is
+# a different model) and evicted least-recently-used.
+_MODEL_CACHE_SIZE = 8
+_mlp_cache: "dict[bytes, int]" = {}
+_lstm_cache: "dict[bytes, int]" = {}
+
+
+def _digest(arrays, extra=()) -> bytes:
+    import hashlib
+
+    import numpy as np
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    h.update(repr(tuple(extra)).encode())
+    return h.digest()
+
+
+def cached_mlp(model) -> int:
+    """Handle of `model` (nvd.weights.MlpModel) on the process-wide Simulator, loading it at most once."""
+    sim = get_sim()
+    key = _digest(list(model.Ws) + list(model.bs), [int(a) for a in model.acts])
+    with _lock:
+        if key in _mlp_cache:
+            _mlp_cache[key] = _mlp_cache.pop(key)          # most recently used last
+            return _mlp_cache[key]
+    h = sim.load_mlp(model)
+    with _lock:
+        _mlp_cache[key] = h
+        while len(_mlp_cache) > _MODEL_CACHE_SIZE:
+            old = _mlp_cache.pop(next(iter(_mlp_cache)))
+            sim.lib.nvd_mlp_free(sim.ctx, old)
+    return h
+
+
+def cached_lstm(model) -> int:
+    sim = get_sim()
+    key = _digest([model.enc_W, model.enc_b, model.dec_W, model.dec_b, model.lin_w, model.lin_b])
+    with _lock:
+        if key in _lstm_cache:
+            _lstm_cache[key] = _lstm_cache.pop(key)
+            return _lstm_cache[key]
+    h = sim.load_lstm(model)
+    with _lock:
+        _lstm_cache[key] = h
+        while len(_lstm_cache) > _MODEL_CACHE_SIZE:
+            old = _lstm_cache.pop(next(iter(_lstm_cache)))
+            sim.lib.nvd_lstm_free(sim.ctx, old)
+    return h
+
+
 def shutdown() -> None:
     global _sim
     with _lock:
+        _mlp_cache.clear()
+        _lstm_cache.clear()
         if _sim is not None:
             _sim.close()
             _sim = None

@@ -121,6 +121,35 @@ def load_default_fnn() -> MlpModel:
     return m
 
 
+FNN_57 = os.path.join(WEIGHTS_DIR, "fnn_57_L7.npz")
+BITWISE = os.path.join(WEIGHTS_DIR, "bitwise_133171_L512_bit0.npz")
+RNN = os.path.join(WEIGHTS_DIR, "rnn_133171_L100.npz")
+
+
+def load_fnn_57() -> MlpModel:
+    """Trained 14-128-64-32-128 tanh decoder for the reference's (7,5) encoder, quirk included
+    (BASELINE.json configs[0]; tools/train_fnn.py --code 57)."""
+    return load_mlp(FNN_57)
+
+
+def load_default_bitwise() -> MlpModel:
+    """Per-bit predictor 1036-30-2 (ReLU, ReLU) for bit 0, start state 0 (tools/train_long_frame_decoders.py bitwise),
+    else seed-fixed reference-initialised weights."""
+    if os.path.exists(BITWISE):
+        return load_mlp(BITWISE)
+    m = init_mlp([1036, 30, 2], ["relu", "relu"], seed=20170711)
+    m.bs = [np.full(b.shape, 0.05, np.float32) for b in m.bs]
+    return m
+
+
+def load_default_lstm() -> LstmModel:
+    """LSTM(20) seq2seq for L = 100 (tools/train_long_frame_decoders.py rnn), else seed-fixed Glorot weights."""
+    if os.path.exists(RNN):
+        z = np.load(RNN)
+        return LstmModel(**{k: z[k].astype(np.float32) for k in ("enc_W", "enc_b", "dec_W", "dec_b", "lin_w", "lin_b")})
+    return init_lstm(20, seed=20170712)
+
+
 def init_lstm(H=20, seed=None) -> LstmModel:
     rng = np.random.default_rng(seed)
 

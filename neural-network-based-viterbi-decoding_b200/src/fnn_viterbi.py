@@ -152,11 +152,8 @@ def multilayer_perceptron(x, weights: Dict, biases: Dict, precision: Optional[st
     """out = tanh(tanh(tanh(tanh(x W1 + b1) W2 + b2) W3 + b3) Wout + bout) — tanh on the output too
     (fnn_viterbi.py:495-508) — evaluated on the GPU; returns numpy [B, n_classes]."""
     sim = runtime.get_sim()
-    h = sim.load_mlp(_model_from(weights, biases))
-    try:
-        _, soft = sim.decode(h, np.asarray(x, dtype=np.float32), _pick_precision(sim, h, precision))
-    finally:
-        _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
+    h = runtime.cached_mlp(_model_from(weights, biases))      # loaded once per distinct parameter set
+    _, soft = sim.decode(h, np.asarray(x, dtype=np.float32), _pick_precision(sim, h, precision))
     return soft
 
 
@@ -170,11 +167,8 @@ def _pick_precision(sim, h, precision):
 def predict(x, weights: Dict, biases: Dict, precision: Optional[str] = None) -> np.ndarray:
     """argmax(multilayer_perceptron(x), 1) — the decode of fnn_viterbi.py:606-610 — as int64 [B]."""
     sim = runtime.get_sim()
-    h = sim.load_mlp(_model_from(weights, biases))
-    try:
-        pred, _ = sim.decode(h, np.asarray(x, dtype=np.float32), _pick_precision(sim, h, precision), want_soft=False)
-    finally:
-        _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
+    h = runtime.cached_mlp(_model_from(weights, biases))
+    pred, _ = sim.decode(h, np.asarray(x, dtype=np.float32), _pick_precision(sim, h, precision), want_soft=False)
     return pred.astype(np.int64)
 
 

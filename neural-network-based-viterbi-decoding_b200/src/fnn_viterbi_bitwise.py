@@ -122,11 +122,9 @@ def _wired_model(weights: Dict, biases: Dict) -> _weights.MlpModel:
 
 def _forward(x, weights, biases):
     sim = runtime.get_sim()
-    h = sim.load_mlp(_wired_model(weights, biases))
-    try:
-        return sim.decode(h, np.asarray(x, dtype=np.float32), "fp32")
-    finally:
-        _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
+    h = runtime.cached_mlp(_wired_model(weights, biases))
+    # runtime.set_precision("bf16") routes to the K-streamed tcgen05 kernel (bf16 rows x bf16 W1, fp32 tail)
+    return sim.decode(h, np.asarray(x, dtype=np.float32), "bf16" if runtime.precision() == "bf16" else "fp32")
 
 
 def train_and_evaluate(config: BitwiseDecoderConfig, train_info, train_encoded, test_info, test_encoded,
@@ -157,7 +155,9 @@ def train_and_evaluate(config: BitwiseDecoderConfig, train_info, train_encoded, 
         print(f"Model saved to {model_save_path}")
     predictions, _ = _forward(test_encoded, weights, biases)
     predictions = predictions.astype(np.int64)
-    errors = int(np.sum(predictions != test_labels))
+    # decision against info bit `bit_position` on the GPU (K5, nvd_count_bit_errors) — :504-509
+    counters = runtime.get_sim().count_bit_errors(predictions, np.asarray(test_info).astype(np.uint8), config.bit_position)
+    errors = int(counters[0])
     error_rate = errors / len(predictions)
     print(f"Test Error Rate: {error_rate:.6f}")
     print(f"Test Accuracy: {1 - error_rate:.6f}")

@@ -112,14 +112,11 @@ def build_network(x, config: SequentialDecoderConfig, weights: Optional[Dict] = 
 
 def _forward(x, weights, biases):
     sim = runtime.get_sim()
-    h = sim.load_mlp(_weights.from_dicts(weights, biases, ["tanh"] * 5))
-    try:
-        # fp32 parity path by default; runtime.set_precision("bf16") / NVD_PRECISION=bf16 selects the wide-layer
-        # tcgen05 kernel (18x faster on B200, 2e-2 tolerance)
-        prec = "bf16" if runtime.precision() == "bf16" and sim.mlp_tc_supported(h) else "fp32"
-        return sim.decode(h, np.asarray(x, dtype=np.float32), prec)
-    finally:
-        _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
+    h = runtime.cached_mlp(_weights.from_dicts(weights, biases, ["tanh"] * 5))
+    # fp32 parity path by default; runtime.set_precision("bf16") / NVD_PRECISION=bf16 selects the wide-layer
+    # tcgen05 kernel (18x faster on B200, 2e-2 tolerance)
+    prec = "bf16" if runtime.precision() == "bf16" and sim.mlp_tc_supported(h) else "fp32"
+    return sim.decode(h, np.asarray(x, dtype=np.float32), prec)
 
 
 def train_and_evaluate(config: SequentialDecoderConfig, train_info, train_encoded, test_info, test_encoded,

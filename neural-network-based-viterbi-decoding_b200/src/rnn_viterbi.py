@@ -112,7 +112,7 @@ def decode(config: RNNDecoderConfig, params: Dict[str, np.ndarray], encoded: np.
     (autoregressive).  -> (logits [B, 2L] fp32, hard bits [B, 2L] uint8)."""
     sim = runtime.get_sim()
     B, T = np.asarray(encoded).shape
-    h = sim.load_lstm(_weights.LstmModel(**{k: np.asarray(v, np.float32) for k, v in params.items()}))
+    h = runtime.cached_lstm(_weights.LstmModel(**{k: np.asarray(v, np.float32) for k, v in params.items()}))
     d_y = sim.to_device(np.ascontiguousarray(encoded, dtype=np.float32))
     d_dec = sim.to_device(np.ascontiguousarray(decoder_inputs, dtype=np.float32)) if decoder_inputs is not None else None
     # fast_math: False / 0 = fp32 parity path, True / 1 = fp32 with MUFU approximations, 2 = bf16 tcgen05 recurrence;
@@ -126,7 +126,6 @@ def decode(config: RNNDecoderConfig, params: Dict[str, np.ndarray], encoded: np.
     for b in (d_y, d_dec, logits_b, hard_b):
         if b is not None:
             sim.free(b)
-    sim.lib.nvd_lstm_free(sim.ctx, h)
     return logits, hard
 
 
@@ -151,7 +150,8 @@ def train_seq2seq(config: RNNDecoderConfig, train_info, train_encoded, test_info
     predictions = hard[:, :L] if config.decision == "sign" else np.zeros((len(hard), L), dtype=np.uint8)
     info_binary = np.asarray(test_info).copy()
     info_binary[info_binary == -1] = 0
-    bit_errors = int(np.sum(np.logical_xor(predictions, info_binary)))
+    # BER over the first L decoder steps on the GPU (K5 on packed rows, nvd_count_row_errors) — :477-491
+    bit_errors = int(runtime.get_sim().count_row_errors(predictions, info_binary.astype(np.uint8))[0])
     total_bits = config.test_size * L
     ber = bit_errors / total_bits
     print(f"Bit Error Rate: {ber:.6f}")

@@ -139,3 +139,51 @@ def test_bad_arguments_fail_loudly(sim, handle):
         sim.run(99, "133171", 7, [1.0], 10)                  # bad handle
     with pytest.raises(NvdError):
         sim.run(handle, "133171", 7, [1.0], 10, mode="fused", precision="fp32")
+
+
+# ------------------------------------------------------------------ BER-curve parity (north-star criterion)
+def _sweep_against_oracle(sim, model, code_name, code, snrs, frames):
+    from nvd import montecarlo as mc
+    h = sim.load_mlp(model)
+    fp32 = sim.run(h, code_name, 7, snrs, frames, 0, mode="staged", precision="fp32", y_dtype="f32")
+    bf16 = sim.run(h, code_name, 7, snrs, frames, 0, mode="fused")
+    prev = None
+    for i, db in enumerate(snrs):
+        ref, det = opipe.mc_step(model.Ws, model.bs, model.acts, 7, code, float(db), 0, frames, seed=SEED, snr_idx=i,
+                                 noise="philox", precision="fp64", return_detail=True)
+        margin = omlp.top2_margin(det["out"])
+        near = int((margin < 1e-3).sum())
+        # fp32 path: the same decisions except on near-tie frames (|margin| < 1e-3)
+        assert abs(int(fp32[i][1]) - int(ref[1])) <= near and abs(int(fp32[i][0]) - int(ref[0])) <= 7 * near, (db, fp32[i], ref, near)
+        # bf16 tensor-core path: BER inside the oracle's 95 % Monte-Carlo (Wilson) interval on the same frames
+        lo, hi = omet.wilson_interval(int(ref[0]), int(ref[3]))
+        ber = float(bf16[i][0]) / float(bf16[i][3])
+        assert lo <= ber <= hi, (db, ber, lo, hi)
+        flo, fhi = omet.wilson_interval(int(ref[1]), int(ref[2]))
+        assert flo <= float(bf16[i][1]) / float(bf16[i][2]) <= fhi
+        if prev is not None and ref[0] > 50:
+            assert ref[0] < prev                      # BER falls with SNR
+        prev = ref[0]
+    return bf16
+
+
+def test_ber_sweep_133171_matches_oracle(sim, model):
+    """BASELINE.json configs[1] curve: (133,171) FNN, 0..8 dB, 2^18 frames per point, GPU vs CPU oracle on the SAME
+    Philox frames — fp32 counters equal up to near ties, bf16 BER/FER inside the oracle's 95 % interval everywhere."""
+    bf16 = _sweep_against_oracle(sim, model, "133171", oenc.CODE_133171, list(range(0, 9)), 1 << 18)
+    ber = bf16[:, 0] / bf16[:, 3]
+    assert ber[0] > 1e-2 and ber[4] < 1e-3            # a trained decoder (weights fixture), not a random one
+
+
+def test_ber_sweep_57_matches_oracle(sim):
+    """BASELINE.json configs[0]: the reference's (7,5) encoder (quirk included) + FNN decoder, 0..6 dB."""
+    from nvd import weights
+    m57 = weights.load_fnn_57()
+    bf16 = _sweep_against_oracle(sim, m57, "57", oenc.CODE_57_REF, list(range(0, 7)), 1 << 18)
+    # the reference's own test-set size (128 classes x 10 000, src/fnn_viterbi.py:58): fused == staged at that size
+    h = sim.load_mlp(m57)
+    n = 1_280_000
+    a = sim.run(h, "57", 7, [0.0, 3.0, 6.0], n, 0, mode="fused")
+    b = sim.run(h, "57", 7, [0.0, 3.0, 6.0], n, 0, mode="staged", precision="bf16")
+    assert (a == b).all() and a[0, 0] > a[1, 0] > a[2, 0]
+    assert bf16[0, 0] / bf16[0, 3] < 0.2
