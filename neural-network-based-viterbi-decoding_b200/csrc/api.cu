@@ -399,8 +399,8 @@ int nvd_mlp_load(nvd_ctx* ctx, int n_layers, const int* dims, const int* acts, c
     NVD_CUDA(cudaMemcpy(m.b[l], b_host[l], dims[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (tc_shape_supported(m)) NVD_TRY(tc_build_image(ctx, m, W_host, b_host));
+  else if (kstream_supported(m)) NVD_TRY(kstream_build_image(m, W_host, b_host));     // tall-and-skinny two-layer nets
   else if (wide_tc_supported(m)) NVD_TRY(wide_tc_build_image(m, W_host, b_host));
-  else if (kstream_supported(m)) NVD_TRY(kstream_build_image(m, W_host, b_host));
   ctx->mlps.push_back(m);
   *model = static_cast<int>(ctx->mlps.size()) - 1;
   return NVD_OK;

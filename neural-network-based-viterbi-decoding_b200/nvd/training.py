@@ -16,10 +16,13 @@ def _torch():
 
 
 def train_mlp(model, x, y_onehot, *, acts, loss="softmax_ce", beta=0.0, l2_layers=(0, 1, 2), lr=1e-4, epochs=1,
-              batch_size=256, dropout_keep=None, display_step=1, log=print):
+              batch_size=256, dropout_keep=None, display_step=1, log=print, epoch_callback=None):
     """Mini-batch Adam over (x, y_onehot) in the reference's fixed batch order (no shuffling:
     fnn_viterbi.py:579-585).  cost = mean CE(out, y) + beta * sum_l l2_loss(W_l) with
-    tf.nn.l2_loss(W) = sum(W^2)/2.  Updates `model` in place and returns the per-epoch costs."""
+    tf.nn.l2_loss(W) = sum(W^2)/2.  Updates `model` in place and returns the per-epoch costs.
+    ONE optimizer lives across all epochs, as the reference's AdamOptimizer does (fnn_viterbi.py:562-603,
+    production_wrapper.py:141-190).  `epoch_callback(epoch, cost, model)` runs after every epoch with `model`
+    holding the current parameters (evaluation, checkpoints); returning True stops the training (early stopping)."""
     torch, dev = _torch()
     Ws = [torch.nn.Parameter(torch.from_numpy(np.array(W, dtype=np.float32)).to(dev)) for W in model.Ws]
     bs = [torch.nn.Parameter(torch.from_numpy(np.array(b, dtype=np.float32)).to(dev)) for b in model.bs]
@@ -57,6 +60,11 @@ def train_mlp(model, x, y_onehot, *, acts, loss="softmax_ce", beta=0.0, l2_layer
         costs.append(avg)
         if display_step and epoch % display_step == 0:
             log(f"Epoch: {epoch + 1:04d} | cost = {avg:.9f}")
+        if epoch_callback is not None:
+            model.Ws = [W.detach().cpu().numpy() for W in Ws]
+            model.bs = [b.detach().cpu().numpy() for b in bs]
+            if epoch_callback(epoch, avg, model):
+                break
     model.Ws = [W.detach().cpu().numpy() for W in Ws]
     model.bs = [b.detach().cpu().numpy() for b in bs]
     return costs

@@ -24,7 +24,7 @@ for _p in (_HERE, os.path.join(_HERE, "src")):
 from utils.config import ConfigManager  # noqa: E402
 from utils.logger import setup_logger  # noqa: E402
 from utils.metrics import MetricsTracker, EarlyStopping  # noqa: E402
-from utils.checkpoint import CheckpointManager  # noqa: E402
+from utils.checkpoint import CheckpointManager, create_model_saver  # noqa: E402
 
 from fnn_viterbi import (DecoderConfig, train_test_dataset, get_weights, multilayer_perceptron, predict,  # noqa: E402,F401
                          encode133171, modulateAwgn)
@@ -33,13 +33,15 @@ from nvd import training, weights as _weights  # noqa: E402
 
 class ProductionTrainer:
     def __init__(self, config_path: str = "config.yaml"):
-        self.config = ConfigManager(config_path).get()
+        self.config_mgr = ConfigManager(config_path)
+        self.config = self.config_mgr.get()
         c = self.config
         self.logger = setup_logger(name="neural_viterbi", log_level=c.logging_level, log_dir=c.paths.logs_dir,
                                    use_json=(c.logging_format == "json"), log_to_console=c.log_to_console,
                                    log_to_file=c.log_to_file)
         self.metrics_tracker = MetricsTracker(c.model.block_length)
-        self.checkpoint_manager = CheckpointManager(c.paths.checkpoints_dir)
+        self.checkpoint_mgr = CheckpointManager(checkpoint_dir=c.paths.checkpoints_dir, max_to_keep=5)
+        self.checkpoint_manager = self.checkpoint_mgr
         self.early_stopping = (EarlyStopping(patience=c.training.early_stopping_patience,
                                              min_delta=c.training.early_stopping_min_delta, mode="min")
                                if c.training.early_stopping_enabled else None)
@@ -72,35 +74,58 @@ class ProductionTrainer:
         return self.metrics_tracker.calculate_metrics(pred, y_onehot, self.class_bits)
 
     def train(self):
+        """One Adam optimizer over all epochs (production_wrapper.py:141-190); after every epoch the train- and
+        test-set decode + BER/FER count run on the GPU, checkpoints are written when epoch % 10 == 0 or on the last
+        epoch (:237-250), and early stopping watches the test BER (:253-258)."""
         c = self.config.training
         model = _weights.from_dicts(self.weights, self.biases, ["tanh"] * 4)
-        every = getattr(c, "checkpoint_every", 10)
-        for epoch in range(c.epochs):
-            t0 = time.time()
-            cost = training.train_mlp(model, self.train_x, self.train_y, acts=model.acts, loss="softmax_ce",
-                                      beta=c.beta_regularization, l2_layers=(0, 1, 2), lr=c.learning_rate, epochs=1,
-                                      batch_size=c.batch_size, display_step=0)[0]
-            self.weights, self.biases = _weights.to_dicts(model)
+        saver = create_model_saver(max_to_keep=5)
+        state = {"t0": time.time(), "last": -1}
+
+        def after_epoch(epoch, cost, m):
+            self.weights, self.biases = _weights.to_dicts(m)
+            saver.weights, saver.biases = self.weights, self.biases
+            state["last"] = epoch
+            if epoch % max(c.display_step, 1) != 0:
+                state["t0"] = time.time()
+                return False
             train_m = self._evaluate(self.train_x, self.train_y)
             test_m = self._evaluate(self.test_x, self.test_y)
-            dt = time.time() - t0
-            self.metrics_tracker.add_epoch_metrics(epoch + 1, train_m, test_m, loss=cost, epoch_time=dt)
-            if epoch % max(c.display_step, 1) == 0:
-                self.logger.info(f"Epoch {epoch + 1:04d} | cost {cost:.6f} | train BER {train_m.ber:.6f} | "
-                                 f"test BER {test_m.ber:.6f} FER {test_m.fer:.6f} | {dt:.2f}s")
-            if (epoch + 1) % every == 0:
-                self.checkpoint_manager.save_checkpoint((self.weights, self.biases), None, epoch + 1, test_m, self.config)
+            dt = time.time() - state["t0"]
+            self.logger.info(f"Epoch {epoch + 1}/{c.epochs} | Time: {dt:.2f}s | Loss: {cost:.6f}")
+            self.logger.info(f"  Train: {train_m}")
+            self.logger.info(f"  Test:  {test_m}")
+            self.metrics_tracker.add_epoch_metrics(epoch=epoch + 1, train_metrics=train_m, val_metrics=test_m, train_loss=cost,
+                                                   epoch_time=dt)
+            if epoch % 10 == 0 or epoch == c.epochs - 1:
+                path = self.checkpoint_mgr.save_checkpoint(
+                    saver=saver, session=None, epoch=epoch + 1,
+                    metrics={"ber": test_m.ber, "fer": test_m.fer, "accuracy": test_m.accuracy, "loss": cost},
+                    config=self.config_mgr._config_to_dict(self.config))
+                self.logger.info(f"Checkpoint saved: {path}")
+            state["t0"] = time.time()
             if self.early_stopping is not None and self.early_stopping(test_m.ber):
-                self.logger.info(f"Early stopping at epoch {epoch + 1}")
-                break
+                self.logger.info(f"Early stopping triggered at epoch {epoch + 1}")
+                return True
+            return False
+
+        training.train_mlp(model, self.train_x, self.train_y, acts=model.acts, loss="softmax_ce", beta=c.beta_regularization,
+                           l2_layers=(0, 1, 2), lr=c.learning_rate, epochs=c.epochs, batch_size=c.batch_size, display_step=0,
+                           epoch_callback=after_epoch)
+        self.weights, self.biases = _weights.to_dicts(model)
+        self.logger.info("Training completed!")
         final = self._evaluate(self.test_x, self.test_y)
-        self.logger.info(f"Final test BER {final.ber:.6f} FER {final.fer:.6f} accuracy {final.accuracy:.4f}")
+        self.logger.info(f"Final metrics: {final}")
         os.makedirs(self.config.paths.models_dir, exist_ok=True)
-        _weights.save_mlp(os.path.join(self.config.paths.models_dir, "final_model.npz"), model)
-        self.metrics_tracker.save_history(os.path.join(self.config.paths.results_dir, "training_history.json"))
-        best = self.checkpoint_manager.get_best_checkpoint(metric="ber")
+        final_path = os.path.join(self.config.paths.models_dir, "final_model.npz")
+        _weights.save_mlp(final_path, model)
+        self.logger.info(f"Final model saved: {final_path}")
+        history_path = os.path.join(self.config.paths.results_dir, "training_history.json")
+        self.metrics_tracker.save_history(history_path)
+        self.logger.info(f"Metrics history saved: {history_path}")
+        best = self.checkpoint_mgr.get_best_checkpoint(metric="ber")
         if best:
-            self.logger.info(f"Best checkpoint: {best}")
+            self.logger.info(f"Best checkpoint: Epoch {best['epoch']} with BER {best['metrics']['ber']:.6f}")
         self.final_metrics = final
         return self
 

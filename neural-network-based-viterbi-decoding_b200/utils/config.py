@@ -45,3 +45,8 @@ class ConfigManager:
 
     def get(self) -> Config:
         return self._config
+
+    @staticmethod
+    def _config_to_dict(config) -> dict:
+        """What the wrapper stores next to a checkpoint (production_wrapper.py:248)."""
+        return config.to_dict() if hasattr(config, "to_dict") else dict(config)

@@ -22,6 +22,9 @@ class Metrics:
     def to_dict(self):
         return asdict(self)
 
+    def __str__(self):
+        return f"BER={self.ber:.6f} FER={self.fer:.6f} Acc={self.accuracy:.4f}"
+
 
 class MetricsTracker:
     def __init__(self, block_length: int):
@@ -39,19 +42,25 @@ class MetricsTracker:
         return Metrics(ber=be / (n * self.block_length), fer=fe / n, accuracy=1.0 - fe / n, bit_errors=be, frame_errors=fe,
                        total_bits=n * self.block_length, total_frames=n)
 
-    def add_epoch_metrics(self, epoch: int, train_metrics=None, test_metrics=None, loss=None, epoch_time=None, **extra):
-        rec = {"epoch": epoch, "loss": loss, "epoch_time": epoch_time}
+    def add_epoch_metrics(self, epoch: int, train_metrics=None, test_metrics=None, loss=None, epoch_time=None,
+                          val_metrics=None, train_loss=None, **extra):
+        """The wrapper's call (production_wrapper.py:229-234) names the test metrics `val_metrics` and the cost
+        `train_loss`; both spellings are accepted."""
+        test_metrics = test_metrics if test_metrics is not None else val_metrics
+        loss = loss if loss is not None else train_loss
+        rec = {"epoch": epoch, "loss": None if loss is None else float(loss), "epoch_time": epoch_time}
         if train_metrics is not None:
             rec["train"] = train_metrics.to_dict() if hasattr(train_metrics, "to_dict") else train_metrics
         if test_metrics is not None:
             rec["test"] = test_metrics.to_dict() if hasattr(test_metrics, "to_dict") else test_metrics
-        rec.update(extra)
+        rec.update({k: (v.to_dict() if hasattr(v, "to_dict") else v) for k, v in extra.items()})
         self.history.append(rec)
 
-    def save_history(self, path: str):
+    def save_history(self, path):
+        path = str(path)
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         with open(path, "w") as f:
-            json.dump(self.history, f, indent=2)
+            json.dump(self.history, f, indent=2, default=str)
 
 
 class EarlyStopping:

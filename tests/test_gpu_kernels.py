@@ -216,7 +216,7 @@ def test_mlp_tensor_core_matches_oracle(sim, B):
 
 def test_mlp_tensor_core_unsupported_shape_fails_loudly(sim):
     from nvd import NvdError
-    for dims in ([14, 600, 128], [1036, 30, 2], [14, 64, 256]):     # a layer wider than 511 / more than 128 classes
+    for dims in ([14, 600, 128], [1036, 100, 2], [14, 64, 256]):    # a layer wider than 511 / more than 128 classes
         m = _model(dims, [1, 1], seed=3)
         h = sim.load_mlp(m)
         assert not sim.mlp_tc_supported(h)
@@ -486,7 +486,7 @@ def test_mlp_tensor_core_matches_reference_graph(sim, golden_fwd, name, builder,
     scale = max(1.0, np.abs(ref).max())       # ReLU logits of the bitwise net are not bounded by 1
     assert np.abs(soft - ref).max() <= 2e-2 * scale
     ok = omlp.top2_margin(ref) >= 5e-2 * scale
-    assert ok.sum() > 0.3 * len(ok) and (pred[ok] == ref_pred[ok]).all()
+    assert ok.sum() > 50 and (pred[ok] == ref_pred[ok]).all()
 
 
 @pytest.mark.parametrize("fast_math,tol", [(0, 2e-5), (2, 3e-2)])

@@ -54,7 +54,7 @@ def test_state_prefix_and_bit_counters(sim):
 
 @pytest.mark.parametrize("dims,acts,B", [([1036, 30, 2], [2, 2], 1), ([1036, 30, 2], [2, 2], 5000), ([1040, 30, 2], [2, 2], 129),
                                          ([1038, 30, 2], [2, 2], 257), ([100, 64, 8], [1, 0], 127), ([48, 16, 2], [1, 1], 1000),
-                                         ([2000, 33, 3], [2, 1], 700)])
+                                         ([1200, 20, 3], [2, 1], 700)])
 def test_kstream_tensor_core_matches_oracle(sim, dims, acts, B):
     """bf16 rows x bf16 W1 on tcgen05 with fp32 accumulation, the tail in fp32: against the fp64 oracle on the same
     bf16-rounded inputs within 2e-2 of the output scale, and tighter against the oracle with W1 rounded to bf16.
