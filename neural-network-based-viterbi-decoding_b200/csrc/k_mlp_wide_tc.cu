@@ -361,228 +361,6 @@ done:
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-// ---- CTA-pair form of a hidden layer (cta_group::2) -----------------------------------------------------
-// Two CTAs of a cluster (one TPC) run ONE M = 256 MMA stream: each keeps its own 128-row tile in its own tensor
-// memory (A, TS mode) and its own accumulators, but the B operand of every instruction is split between them —
-// each CTA's ring holds 64 of the chunk's 128 output columns — so every SM ingests HALF of the layer image per
-// tile, which is what bounds mlp_wide_layer_kernel.  Only the leader (cluster rank 0) issues; its barriers collect
-// arrivals from both CTAs (row warps: A ready, accumulator drained; rank 1's warp 9 relays "my half of stage s has
-// landed"), and its tcgen05.commit is multicast to both CTAs (stage free, accumulator full).
-// Hidden layers only (every chunk is 128 columns wide: Np is a multiple of 256); the image's second half holds the
-// pair layout [chunk][half][Kp/8][64][8].
-constexpr int kPairStages = 12;
-constexpr int kPairStageBytes = 64 * kStageK * 2;     // 8 KB: this CTA's 64 output columns x 64 k
-static_assert(kPairStages * kPairStageBytes == kStages * kStageBytes, "same ring footprint as the single-CTA kernel");
-constexpr int kPairBarBytes = 8 * (3 * kPairStages + 2 + 2 + 3) + 8;
-
-__global__ void __launch_bounds__(kThreads, 1) mlp_wide_pair_kernel(const WideParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = ptx::smem_u32(smem);
-  const int tid = threadIdx.x;
-  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-  constexpr int A_OFF = kPairStages * kPairStageBytes;
-  constexpr int BAR_OFF = A_OFF + kAOperandBytes;
-  const uint32_t bar_full = sbase + BAR_OFF;                        // [S] my half of stage s has landed (local)
-  const uint32_t bar_pfull = bar_full + 8 * kPairStages;            // [S] leader: the peer's half has landed
-  const uint32_t bar_empty = bar_pfull + 8 * kPairStages;           // [S] the pair's MMAs have read stage s
-  const uint32_t bar_dfull = bar_empty + 8 * kPairStages;           // [2] accumulator complete (both CTAs)
-  const uint32_t bar_dfree = bar_dfull + 16;                        // [2] leader: drained by both CTAs' epilogues
-  const uint32_t bar_aready = bar_dfree + 16;                       // leader: both tiles' rows are in tensor memory
-  const uint32_t bar_xfull = bar_aready + 8;
-  const uint32_t bar_xempty = bar_xfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 8 * (3 * kPairStages + 2 + 2 + 3));
-
-  if (tid == 0) {
-    for (int s = 0; s < kPairStages; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_pfull + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar_dfull + 8 * b, 1); ptx::mbar_init(bar_dfree + 8 * b, 8); }
-    ptx::mbar_init(bar_aready, 16);
-    ptx::mbar_init(bar_xfull, 1);
-    ptx::mbar_init(bar_xempty, 8);
-    ptx::mbar_fence_init();
-  }
-  __syncthreads();
-  ptx::cluster_sync();      // both CTAs' barriers exist before the pair allocates / anything arrives remotely
-  if (warp == 0) { ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish_pair(); }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
-  const uint32_t crank = ptx::cluster_ctarank();
-  const bool leader = crank == 0;
-
-  const int64_t real_tiles = (p.B + 127) >> 7;
-  const int64_t num_tiles = (real_tiles + gridDim.x - 1) / gridDim.x * gridDim.x;   // both CTAs walk the same count
-  const int n_chunks = p.Np >> 7;
-  const int k_stages = p.Kp / kStageK;
-  const uint8_t* Wp = p.W + static_cast<size_t>(p.Kp) * p.Np * 2;                    // pair-layout copy of the image
-
-  if (warp == 8) {
-    // ---- producer: my half of every stage, and the next tile's rows ----
-    if (ptx::elect_one()) {
-      uint32_t it = 0, xt = 0;
-      const uint32_t x_bytes = 128u * static_cast<uint32_t>(p.Kp) * 2u;
-      auto stage_rows = [&](int64_t t) {
-        if (t >= real_tiles) { ptx::mbar_arrive(bar_xfull); return; }
-        ptx::mbar_arrive_expect_tx(bar_xfull, x_bytes);
-        for (uint32_t o = 0; o < x_bytes; o += 32768)
-          ptx::bulk_g2s(sbase + A_OFF + o, reinterpret_cast<const uint8_t*>(p.X) + static_cast<size_t>(t) * x_bytes + o, 32768, bar_xfull);
-      };
-      if (static_cast<int64_t>(blockIdx.x) < num_tiles) stage_rows(blockIdx.x);
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++xt) {
-        if (tile + gridDim.x < num_tiles) {
-          if (!ptx::mbar_wait_bounded(bar_xempty, xt & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 45); goto done; }
-          stage_rows(tile + gridDim.x);
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-          const uint8_t* src = Wp + (static_cast<size_t>(2 * c + crank) * (p.Kp / 8)) * (64 * 16);
-          for (int ks = 0; ks < k_stages; ++ks, ++it) {
-            const int s = it % kPairStages;
-            if (!ptx::mbar_wait_bounded(bar_empty + 8 * s, ((it / kPairStages) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 40); goto done; }
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kPairStageBytes);
-            ptx::bulk_g2s(sbase + s * kPairStageBytes, src + static_cast<size_t>(ks) * kPairStageBytes, kPairStageBytes, bar_full + 8 * s);
-          }
-        }
-      }
-    }
-  } else if (warp == 9) {
-    if (!leader) {
-      // ---- relay: lane s tells the leader whenever my half of stage s has landed (one lane per stage: a remote
-      //      arrival has a long latency, so the stages' notifications must be in flight side by side) ----
-      const int s = tid & 31;
-      if (s < kPairStages) {
-        const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-        const int64_t total = my_tiles * n_chunks * k_stages;
-        uint32_t use = 0;
-        for (int64_t i = s; i < total; i += kPairStages, ++use) {
-          if (!ptx::mbar_wait_bounded(bar_full + 8 * s, use & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 46); break; }
-          ptx::mbar_arrive_remote_relaxed(bar_pfull + 8 * s, 0);
-        }
-      }
-    } else if (ptx::elect_one()) {
-      uint32_t it = 0;
-      {
-        // ---- MMA issuer of the pair ----
-        uint32_t tile_it = 0, chunk_it = 0;
-        const bool dbg = (NVD_WIDE_TIMING_ALWAYS != 0) || p.debug != nullptr;
-        long long t_a = 0, t_d = 0, t_f = 0, t_p = 0, t_i = 0, t0 = clock64(), tt = 0;
-        constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, 128);
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-          if (dbg) tt = clock64();
-          if (!ptx::mbar_wait_bounded(bar_aready, tile_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 41); goto done; }
-          if (dbg) t_a += clock64() - tt;
-          ptx::tc_fence_after();
-          for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
-            const int buf = chunk_it & 1;
-            if (dbg) tt = clock64();
-            if (!ptx::mbar_wait_bounded(bar_dfree + 8 * buf, ((chunk_it >> 1) & 1) ^ 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 42); goto done; }
-            if (dbg) t_d += clock64() - tt;
-            ptx::tc_fence_after();
-            for (int ks = 0; ks < k_stages; ++ks, ++it) {
-              const int s = it % kPairStages;
-              const uint32_t par = (it / kPairStages) & 1;
-              if (dbg) tt = clock64();
-              if (!ptx::mbar_wait_bounded(bar_full + 8 * s, par, kMaxWaitMs)) { atomicExch(p.abort_flag, 43); goto done; }
-              if (dbg) t_f += clock64() - tt;
-              if (dbg) tt = clock64();
-              if (!ptx::mbar_wait_bounded(bar_pfull + 8 * s, par, kMaxWaitMs)) { atomicExch(p.abort_flag, 47); goto done; }
-              if (dbg) t_p += clock64() - tt;
-              if (dbg) tt = clock64();
-              ptx::tc_fence_after();
-#pragma unroll
-              for (int j = 0; j < kStageK / 16; ++j)
-                ptx::umma_f16_ts_pair(tmem_base + 128 * buf, tmem_base + COL_A + 8 * (ks * (kStageK / 16) + j),
-                                      ptx::make_smem_desc16(((sbase & 0x3FFFFu) >> 4) + s * (kPairStageBytes >> 4), j * 2 * (64 * 16), 64 * 16, 128), idesc,
-                                      (ks | j) != 0);
-              ptx::umma_commit_pair(bar_empty + 8 * s, 3);
-              if (dbg) t_i += clock64() - tt;
-            }
-            ptx::umma_commit_pair(bar_dfull + 8 * buf, 3);
-          }
-        }
-        if (p.debug != nullptr && blockIdx.x == 0) {
-          p.debug[0] = clock64() - t0; p.debug[1] = t_a; p.debug[2] = t_d; p.debug[3] = t_f; p.debug[4] = t_i; p.debug[5] = tile_it; p.debug[6] = t_p;
-        }
-      }
-    }
-  } else {
-    // ---- rows and epilogues: as in mlp_wide_layer_kernel, arrivals for the issuer go to the leader ----
-    const int set = warp >> 2;
-    const int r = (warp & 3) * 32 + (tid & 31);
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    uint32_t chunk_it = 0, rows_it = 0;
-    auto load_rows = [&]() -> bool {
-      if (!ptx::mbar_wait_bounded(bar_xfull, rows_it & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 48); return false; }
-      ++rows_it;
-      for (int b = set; b < p.Kp / 256; b += 2) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t w[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + A_OFF + (32 * b + 4 * c + q) * 2048 + r * 16);
-            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-          }
-          ptx::tmem_st16(tmem_base + lane_base + COL_A + 128 * b + 16 * c, w);
-        }
-      }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        ptx::mbar_arrive(bar_xempty);
-        ptx::mbar_arrive_remote(bar_aready, 0);
-      }
-      return true;
-    };
-    auto epilogue = [&](int64_t tile, int c, int buf) {
-      const uint32_t d = tmem_base + lane_base + 128 * buf;
-      __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.Y) + (static_cast<size_t>(tile) * (p.Np / 8) + 16 * c) * 1024 + r * 8;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(d + c0, v);
-        ptx::tmem_wait_ld();
-        if (tile < real_tiles) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(apply_act(__uint_as_float(v[8 * q]), p.act), apply_act(__uint_as_float(v[8 * q + 1]), p.act));
-            o.y = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 2]), p.act), apply_act(__uint_as_float(v[8 * q + 3]), p.act));
-            o.z = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 4]), p.act), apply_act(__uint_as_float(v[8 * q + 5]), p.act));
-            o.w = pack_bf16x2(apply_act(__uint_as_float(v[8 * q + 6]), p.act), apply_act(__uint_as_float(v[8 * q + 7]), p.act));
-            *reinterpret_cast<uint4*>(out + ((c0 >> 3) + q) * 1024) = o;
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if ((tid & 31) == 0) ptx::mbar_arrive_remote(bar_dfree + 8 * buf, 0);
-    };
-
-    int64_t tile = blockIdx.x;
-    if (tile < num_tiles && !load_rows()) goto done;
-    for (; tile < num_tiles; tile += gridDim.x) {
-      for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
-        const int buf = chunk_it & 1;
-        const bool mine = buf == set, last_chunk = c == n_chunks - 1;
-        if (!mine && !last_chunk) continue;
-        if (!ptx::mbar_wait_bounded(bar_dfull + 8 * buf, (chunk_it >> 1) & 1, kMaxWaitMs)) { atomicExch(p.abort_flag, 44); goto done; }
-        ptx::tc_fence_after();
-        if (last_chunk && tile + gridDim.x < num_tiles && !load_rows()) goto done;
-        if (mine) epilogue(tile, c, buf);
-      }
-    }
-  }
-done:
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync();
-  if (warp == 0) ptx::tmem_dealloc_pair(tmem_base, 512);
-}
-
 // rows of the first layer: dense ([B, K] with row stride K) or overlapping windows of one stream (row stride =
 // window stride, e.g. 2), converted to bf16, 1.0 at column K, zero padding up to Kp
 template <typename T>
@@ -652,16 +430,6 @@ int wide_tc_build_image(MlpModel& m, const float* const* W_host, const float* co
       }
       chunk_off += static_cast<size_t>(Kp) * nc;
     }
-    if (!last) {
-      // second copy for the CTA-pair kernel: [chunk][half][Kp/8][64][8] — each CTA's half of a stage is contiguous
-      const size_t base = img.size();
-      img.resize(2 * base, 0);
-      for (int c = 0; c * 128 < Np; ++c)
-        for (int nn = 0; nn < 128; ++nn)
-          for (int k = 0; k < Kp; ++k)
-            img[base + (static_cast<size_t>(2 * c + nn / 64) * (Kp / 8) + (k >> 3)) * 512 + (nn % 64) * 8 + (k & 7)] =
-                img[static_cast<size_t>(c) * Kp * 128 + static_cast<size_t>(k >> 3) * 1024 + nn * 8 + (k & 7)];
-    }
     NVD_CUDA(cudaMalloc(&m.wide_image[l], img.size() * 2));
     NVD_CUDA(cudaMemcpy(m.wide_image[l], img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -708,13 +476,6 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
   NVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles));
   if (cluster > 1) grid = ctx->sm_count;
-  // CTA pairs (cta_group::2) for the hidden layers: each SM ingests half of the layer image per tile
-  const char* pair_env = getenv("NVD_WIDE_PAIR");     // opt-in: 1 = when every SM has a tile, 2 = always (tests)
-  const int want_pair = pair_env ? atoi(pair_env) : 0;
-  const bool pair_ok = want_pair && ctx->sm_count % 2 == 0 && (tiles >= ctx->sm_count || want_pair == 2);   // 2: forced (tests)
-  const int pair_grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, (tiles + 1) / 2 * 2));
-  const int pair_smem = kPairStages * kPairStageBytes + kAOperandBytes + kPairBarBytes;
-  if (pair_ok) NVD_CUDA(cudaFuncSetAttribute(mlp_wide_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
   for (int l = 0; l < m.n_layers; ++l) {
     WideParams p{};
     const bool last = l == m.n_layers - 1;
@@ -736,27 +497,25 @@ int launch_mlp_wide_tc(nvd_ctx* ctx, const MlpModel& m, const void* src, int src
       if (!dbg) cudaMalloc(&dbg, 64);
       p.debug = dbg;
     }
-    const bool pair = pair_ok && !last;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pair ? pair_grid : grid);
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = pair ? pair_smem : smem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : cluster;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (pair) NVD_CUDA(cudaLaunchKernelEx(&cfg, mlp_wide_pair_kernel, p));
-    else NVD_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    NVD_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     if (p.debug) {
-      unsigned long long h[7];
-      cudaMemcpyAsync(h, dbg, 56, cudaMemcpyDeviceToHost, ctx->stream);
+      unsigned long long h[6];
+      cudaMemcpyAsync(h, dbg, 48, cudaMemcpyDeviceToHost, ctx->stream);
       cudaStreamSynchronize(ctx->stream);
-      fprintf(stderr, "wide layer %d%s: rows %lld  issuer clk total %llu  wait a_ready %llu  wait d_free %llu  wait full %llu  issue %llu  tiles %llu  wait peer %llu\n",
-              l, pair ? " (pair)" : "", static_cast<long long>(B), h[0], h[1], h[2], h[3], h[4], h[5], pair ? h[6] : 0ull);
+      fprintf(stderr, "wide layer %d: rows %lld  issuer clk total %llu  wait a_ready %llu  wait d_free %llu  wait full %llu  issue %llu  tiles %llu\n",
+              l, static_cast<long long>(B), h[0], h[1], h[2], h[3], h[4], h[5]);
     }
     std::swap(ping, pong);
   }

@@ -82,48 +82,6 @@ __device__ __forceinline__ bool mbar_spin_bounded(uint32_t bar, uint32_t parity,
   }
 }
 
-// ---- CTA pairs (cta_group::2): barriers that a peer CTA arrives on ---------------------------------
-// wait with cluster-scope acquire: the arrival may come from the other CTA of the pair
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-__device__ __forceinline__ bool mbar_wait_cluster_bounded(uint32_t bar, uint32_t parity, uint32_t max_ms) {
-  if (mbar_try_wait_cluster(bar, parity)) return true;
-  uint64_t t0 = 0;
-  for (uint32_t spin = 1;; ++spin) {
-    if (mbar_try_wait_cluster(bar, parity)) return true;
-    if ((spin & 1023u) == 0u) {
-      const uint64_t now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > static_cast<uint64_t>(max_ms) * 1000000ull) return false;
-    }
-  }
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (default semantics, as
-// CUTLASS ClusterBarrier::arrive(cta_id): cluster-scope release measured slower and is not needed for hand-offs
-// that are ordered by tcgen05 fences)
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-
-// the same without release ordering: for pure notifications (the data was written by the async proxy and its
-// completion already observed through a local mbarrier)
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t cta) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -175,16 +133,6 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// the cta_group::2 forms: one warp of EACH CTA of the pair issues them (same warp index, same slot offset)
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_pair() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -216,24 +164,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // the same arrival on the mbarrier at this offset in every CTA of cta_mask (stage release in a multicast ring)
 __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask)
-               : "memory");
-}
-
-// CTA-pair MMA (issued by the leader CTA only): M = 256 rows = 128 TMEM lanes in each CTA, A from each CTA's own
-// tensor memory, B split by output column: each CTA's shared memory holds N/2 rows of it at the same offset
-__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// completion of the pair's MMAs, signalled on the mbarrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask)
                : "memory");
 }

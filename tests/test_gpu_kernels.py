@@ -361,32 +361,6 @@ def test_mlp_wide_tensor_core_matches_oracle(sim, dims, acts, B):
     assert (pred[ok] == omlp.argmax_first(want64)[ok]).all()
 
 
-@pytest.mark.parametrize("B", [1000, 148 * 128 + 5])
-def test_mlp_wide_cta_pair_equals_single_cta(sim, B):
-    """Opt-in CTA-pair form of the hidden layers (tcgen05.mma.cta_group::2: M = 256 over two SMs, each holding half
-    of every weight stage; NVD_WIDE_PAIR) gives bit-identical outputs to the single-CTA kernel."""
-    import os
-    dims, acts = [200, 500, 500, 500, 500, 2], [1, 1, 1, 1, 1]
-    m = _model(dims, acts, seed=11, bias=0.1)
-    h = sim.load_mlp(m)
-    y = np.random.default_rng(B).standard_normal((B, dims[0])).astype(np.float32)
-    d_y = sim.to_device(y)
-    outs = []
-    for mode in (None, "2"):
-        if mode is None:
-            os.environ.pop("NVD_WIDE_PAIR", None)
-        else:
-            os.environ["NVD_WIDE_PAIR"] = mode
-        try:
-            soft_b, hard_b = sim.mlp_forward(h, d_y, "f32", B, 2, "bf16", want_soft=True, hard_bytes=4)
-            outs.append((soft_b.download(np.float32, (B, 2)), hard_b.download(np.int32, (B,))))
-        finally:
-            os.environ.pop("NVD_WIDE_PAIR", None)
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-    want64 = omlp.forward(y.astype(np.float32), m.Ws, m.bs, m.acts, dtype=np.float64)
-    assert np.abs(outs[1][0] - want64).max() <= 2e-2
-
-
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_window_decode_matches_dense_rows(sim, precision):
     """nvd_window_decode over a stride-2 stream == the same windows decoded as dense rows (get_single_instance,
