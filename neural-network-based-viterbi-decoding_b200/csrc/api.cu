@@ -849,7 +849,9 @@ int nvd_mc_run_bitwise(nvd_ctx* ctx, const nvd_mc_bitwise_config* cfg, const flo
     return NVD_OK;
   }
   const int64_t chunk = std::min<int64_t>(static_cast<int64_t>(cfg->frames), int64_t(1) << 18);
-  const size_t S_in = (cfg->L + 7) / 8, S_pre = (Lt + 7) / 8, S_c = (n + 7) / 8, ys = static_cast<size_t>(n) * (tc ? 2 : 4);
+  // tensor-core path: rows padded to a multiple of 8 symbols (16 bytes) so that the K-streamed kernel takes them by TMA
+  const int64_t y_stride = tc ? ((n + 7) & ~7) : n;
+  const size_t S_in = (cfg->L + 7) / 8, S_pre = (Lt + 7) / 8, S_c = (n + 7) / 8, ys = static_cast<size_t>(y_stride) * (tc ? 2 : 4);
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
   const size_t o_pre = al(chunk * S_in), o_c = o_pre + al(chunk * S_pre), o_y = o_c + al(chunk * S_c), o_p = o_y + al(chunk * ys);
   NVD_TRY(ensure_mc_buf(ctx, o_p + al(chunk)));
@@ -874,9 +876,9 @@ int nvd_mc_run_bitwise(nvd_ctx* ctx, const nvd_mc_bitwise_config* cfg, const flo
       t.mark();
       NVD_TRY(launch_encode(ctx, cfg->code, d_pre, Lt, nfr, d_coded));
       t.mark();
-      NVD_TRY(launch_channel(ctx, d_coded, n, nfr, sigma, idx, f0, y_dtype, d_y));
+      NVD_TRY(launch_channel(ctx, d_coded, n, nfr, sigma, idx, f0, y_dtype, d_y, y_stride));
       t.mark();
-      if (tc) NVD_TRY(launch_mlp_kstream(ctx, *m, static_cast<const __nv_bfloat16*>(d_y), n, nfr, nullptr, d_pred, 1));
+      if (tc) NVD_TRY(launch_mlp_kstream(ctx, *m, static_cast<const __nv_bfloat16*>(d_y), y_stride, nfr, nullptr, d_pred, 1));
       else NVD_TRY(launch_mlp_fp32(ctx, *m, d_y, storage_dtype(y_dtype), nfr, nullptr, d_pred, 1));
       t.mark();
       NVD_TRY(launch_count_bit(ctx, d_pred, d_info, static_cast<int>(S_in), cfg->bit_position, nfr, counters_dev + 4 * i));

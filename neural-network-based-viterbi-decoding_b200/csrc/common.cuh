@@ -128,8 +128,10 @@ void comm_release(nvd_ctx* ctx);
 // ---- kernel launchers (each validates nothing; the API layer does) -----------------------
 int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed);
 int launch_encode(nvd_ctx* ctx, int code, const uint8_t* info, int L, int64_t B, uint8_t* coded);
+// row_stride: elements between rows of y (0 = dense, n); a stride that is a multiple of 8 bf16 lets the K-streamed
+// decoder take the rows by TMA
 int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float sigma, int snr_idx,
-                   uint64_t frame0, int out_dtype, void* y);
+                   uint64_t frame0, int out_dtype, void* y, int64_t row_stride = 0);
 int launch_mlp_fp32(nvd_ctx* ctx, const MlpModel& m, const void* y, int y_dtype, int64_t B,
                     float* soft_out, void* hard_out, int hard_bytes);
 int launch_count(nvd_ctx* ctx, const void* pred, const void* label, int stride, int L, int64_t B,

@@ -38,7 +38,7 @@ __device__ __forceinline__ typename OutT<kDtype>::type cast_out(float v) {
 template <int kDtype, bool kSmall>
 __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const uint8_t* __restrict__ coded,
                                                       int n, int S, int nblk, int64_t B, float sigma,
-                                                      uint32_t stream_word, uint64_t frame0,
+                                                      uint32_t stream_word, uint64_t frame0, int64_t row_stride,
                                                       typename OutT<kDtype>::type* __restrict__ y) {
   using T = typename OutT<kDtype>::type;
   const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const
   float v[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) v[k] = fmaf(sigma, z[k], ((bits >> k) & 1u) ? 1.0f : -1.0f);
-  T* row = y + f * n + j0;
-  if (j0 + 6 <= n && (n & 1) == 0) {
+  T* row = y + f * row_stride + j0;
+  if (j0 + 6 <= n && (n & 1) == 0 && (row_stride & 1) == 0) {
     // even n: rows start 4 B (bf16) / 8 B (fp32, int32) aligned -> three vector stores
 #pragma unroll
     for (int k = 0; k < 6; k += 2) {
@@ -125,14 +125,15 @@ __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk,
 }
 
 int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float sigma, int snr_idx,
-                   uint64_t frame0, int out_dtype, void* y) {
+                   uint64_t frame0, int out_dtype, void* y, int64_t row_stride) {
   if (B == 0) return NVD_OK;
+  if (row_stride <= 0) row_stride = n;            // dense rows; a padded stride leaves the pad elements untouched
   const int S = (n + 7) / 8, nblk = (n + kNormalsPerBlock - 1) / kNormalsPerBlock;
   const int64_t threads = B * nblk;
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
   const uint32_t sw = noise_stream_word(snr_idx);
   const PhiloxKeys rk = make_philox_keys(ctx->seed);
-  if (n <= 16 && (n & 1) == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0) {   // the frame kernel stores 16-byte vectors
+  if (n <= 16 && (n & 1) == 0 && row_stride == n && reinterpret_cast<uintptr_t>(y) % 16 == 0) {   // the frame kernel stores 16-byte vectors
     const unsigned fgrid = static_cast<unsigned>((B + 255) / 256);
 #define NVD_LAUNCH_FRAME(DT, CT)                                                                                          \
   do {                                                                                                                    \
@@ -155,9 +156,9 @@ int launch_channel(nvd_ctx* ctx, const uint8_t* coded, int n, int64_t B, float s
 #define NVD_LAUNCH_CHANNEL(DT, CT)                                                                                     \
   do {                                                                                                                 \
     if (small) channel_kernel<DT, true><<<grid, 256, 0, ctx->stream>>>(rk, coded, n, S, nblk, B, sigma, sw, frame0,    \
-                                                                       static_cast<CT*>(y));                            \
+                                                                       row_stride, static_cast<CT*>(y));                \
     else channel_kernel<DT, false><<<grid, 256, 0, ctx->stream>>>(rk, coded, n, S, nblk, B, sigma, sw, frame0,         \
-                                                                  static_cast<CT*>(y));                                 \
+                                                                  row_stride, static_cast<CT*>(y));                     \
   } while (0)
   switch (out_dtype) {
     case NVD_F32: NVD_LAUNCH_CHANNEL(NVD_F32, float); break;

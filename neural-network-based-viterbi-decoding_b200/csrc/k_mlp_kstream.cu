@@ -22,7 +22,10 @@
 //     (<= 64 x 8) as fp32 FMAs against broadcast shared-memory weights, activation, argmax (first index on ties);
 //     fused mode compares with the label bit and only four counters leave the SM.
 // All mbarrier waits are bounded (abort flag), as in k_mlp_tc.cu.
+#include <cuda.h>      // CUtensorMap and its enums only: the encoder is fetched with cudaGetDriverEntryPoint
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "frame_gen.cuh"
@@ -158,6 +161,48 @@ __device__ __forceinline__ void gen_stage(FrameGen& g, const KsParams& p, int b,
       w[j >> 1] = j < valid_sym ? pack2(a, c) : 0u;
     }
   }
+}
+
+// Tile epilogue of one thread = one frame: the N1pad accumulators of its TMEM lane -> + b1, activation, the small
+// second layer in fp32 against broadcast shared-memory weights, activation, argmax (first index on ties, tf.argmax).
+// Staged outputs are stored here; returns the decision.
+__device__ __forceinline__ int tile_epilogue(const KsParams& p, const float* l2s, uint32_t tmem_d, int64_t row, bool store) {
+  float out[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) out[o] = l2s[p.N1pad + p.N1pad * kMaxOut + o];
+  for (int c = 0; c < p.N1pad; c += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(tmem_d + c, v);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float h = apply_act(__uint_as_float(v[j]) + l2s[c + j], p.act1);
+      const float4 wa = *reinterpret_cast<const float4*>(l2s + p.N1pad + (c + j) * kMaxOut);
+      const float4 wb = *reinterpret_cast<const float4*>(l2s + p.N1pad + (c + j) * kMaxOut + 4);
+      out[0] = fmaf(h, wa.x, out[0]); out[1] = fmaf(h, wa.y, out[1]); out[2] = fmaf(h, wa.z, out[2]); out[3] = fmaf(h, wa.w, out[3]);
+      out[4] = fmaf(h, wb.x, out[4]); out[5] = fmaf(h, wb.y, out[5]); out[6] = fmaf(h, wb.z, out[6]); out[7] = fmaf(h, wb.w, out[7]);
+    }
+  }
+  ptx::tc_fence_before();            // accumulator reads done before the next MMA chain overwrites them
+  int best = 0;
+  float bv = 0.0f;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    if (o < p.n_out) {
+      out[o] = apply_act(out[o], p.act2);
+      if (o == 0 || out[o] > bv) { bv = out[o]; best = o; }     // strict: first index on ties
+    }
+  }
+  if (store && row < p.B) {
+    if (p.soft)
+      for (int o = 0; o < p.n_out; ++o) p.soft[row * p.n_out + o] = out[o];
+    if (p.hard) {
+      if (p.hard_bytes == 1) static_cast<uint8_t*>(p.hard)[row] = static_cast<uint8_t>(best);
+      else if (p.hard_bytes == 2) static_cast<uint16_t*>(p.hard)[row] = static_cast<uint16_t>(best);
+      else static_cast<int32_t*>(p.hard)[row] = best;
+    }
+  }
+  return best;
 }
 
 template <int MODE, int CP>
@@ -304,43 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kstream_kernel(const KsParams
       if (!ptx::mbar_wait_bounded(bar_free + 8 * slot, use & 1u, kMaxWaitMs)) { atomicExch(p.abort_flag, 23); ok = false; break; }
       ptx::tc_fence_after();
       const int64_t row = tile * 128 + r;
-      float out[kMaxOut];
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) out[o] = l2s[p.N1pad + p.N1pad * kMaxOut + o];
-      for (int c = 0; c < p.N1pad; c += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_d + c, v);
-        ptx::tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h = apply_act(__uint_as_float(v[j]) + l2s[c + j], p.act1);
-          const float4 wa = *reinterpret_cast<const float4*>(l2s + p.N1pad + (c + j) * kMaxOut);
-          const float4 wb = *reinterpret_cast<const float4*>(l2s + p.N1pad + (c + j) * kMaxOut + 4);
-          out[0] = fmaf(h, wa.x, out[0]); out[1] = fmaf(h, wa.y, out[1]); out[2] = fmaf(h, wa.z, out[2]); out[3] = fmaf(h, wa.w, out[3]);
-          out[4] = fmaf(h, wb.x, out[4]); out[5] = fmaf(h, wb.y, out[5]); out[6] = fmaf(h, wb.z, out[6]); out[7] = fmaf(h, wb.w, out[7]);
-        }
-      }
-      ptx::tc_fence_before();            // accumulator reads done before the next tile's first MMA overwrites them
-      int best = 0;
-      float bv = 0.0f;
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) {
-        if (o < p.n_out) {
-          out[o] = apply_act(out[o], p.act2);
-          if (o == 0 || out[o] > bv) { bv = out[o]; best = o; }     // strict: first index on ties (tf.argmax)
-        }
-      }
-      if (MODE == KS_STAGED) {
-        if (row < p.B) {
-          if (p.soft)
-            for (int o = 0; o < p.n_out; ++o) p.soft[row * p.n_out + o] = out[o];
-          if (p.hard) {
-            if (p.hard_bytes == 1) static_cast<uint8_t*>(p.hard)[row] = static_cast<uint8_t>(best);
-            else if (p.hard_bytes == 2) static_cast<uint16_t*>(p.hard)[row] = static_cast<uint16_t>(best);
-            else static_cast<int32_t*>(p.hard)[row] = best;
-          }
-        }
-      } else if (row < p.B) {
+      const int best = tile_epilogue(p, l2s, tmem_d, row, MODE == KS_STAGED);
+      if (MODE == KS_FUSED && row < p.B) {
         const uint32_t e = (static_cast<uint32_t>(best) ^ gen.label) & 1u;
         bit_err += e;
         frame_err += e;
@@ -371,6 +381,188 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kstream_kernel(const KsParams
   ptx::tc_fence_before();
   __syncthreads();
   if (tid < 32) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- MODE_STAGED with TMA: rows whose stride is a multiple of 16 bytes --------------------------------------------
+// One `cp.async.bulk.tensor.2d` per stage: a [128 rows x 64 symbols] box of the row-major bf16 matrix lands in shared
+// memory in the SWIZZLE_128B K-major layout the UMMA descriptor names (16 KB; symbols beyond K and rows beyond B are
+// zero-filled by the copy engine), so the stream costs no LSU instructions at all — the cp.async form above is bound by
+// LDGSTS wavefronts at 21 % of HBM.  Per group: a driver warp (waits for a stage, issues its four MMAs, commits, re-arms
+// the stage it just freed) and four epilogue warps that only wake up once per tile; two accumulator buffers per group
+// let the epilogue of tile t overlap the stream of tile t + 1.
+constexpr int kTmaSym = 64;
+constexpr int kTmaStageBytes = 128 * kTmaSym * 2;   // 16 KB
+constexpr int kTmaStages = 2;
+constexpr int kTmaThreads = kThreads + 32 * kGroups;
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr) {
+  // K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO); the K step inside the atom is selected by the
+  // start address (+32 B per 16 elements); LBO is not used by swizzled K-major layouts
+  const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO, descriptor version 1, layout type 2
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1) mlp_kstream_tma_kernel(const KsParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int S = kTmaStages;
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  const bool is_driver = warp >= kThreads / 32;
+  const int g = is_driver ? warp - kThreads / 32 : warp >> 2;
+  const int wq = warp & 3, lane = tid & 31;
+  const int r = tid & 127;
+  const int w_bytes = (p.Kpad / 8) * p.N1pad * 16;
+  const int l2_floats = p.N1pad + p.N1pad * kMaxOut + kMaxOut;
+  const int l2_off = w_bytes;
+  const int bar_off = (l2_off + l2_floats * 4 + 15) & ~15;
+  const int ring_off = (bar_off + 512 + 1023) & ~1023;
+  const uint32_t grp_ring = sbase + ring_off + g * S * kTmaStageBytes;
+  const uint32_t sbase16 = (sbase & 0x3FFFFu) >> 4;
+  const uint32_t bar_full = sbase + bar_off + 64 * g;            // [S] stage landed (expect_tx)
+  const uint32_t bar_free = bar_full + 8 * S;                    // [S] the stage's MMAs have completed
+  const uint32_t bar_done = bar_free + 8 * S;                    // [2] accumulator buffer d holds a finished tile
+  const uint32_t bar_dfree = bar_done + 16;                      // [2] ... and has been read out (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 64 * kGroups);
+  const float* l2s = reinterpret_cast<const float*>(smem + l2_off);
+
+  for (int i = tid; i < w_bytes / 16; i += kTmaThreads) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(p.image) + i);
+  for (int i = tid; i < l2_floats; i += kTmaThreads) reinterpret_cast<float*>(smem + l2_off)[i] = __ldg(p.l2 + i);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) {
+      const uint32_t b0 = sbase + bar_off + 64 * i;
+      for (int s2 = 0; s2 < S; ++s2) { ptx::mbar_init(b0 + 8 * s2, 1); ptx::mbar_init(b0 + 8 * S + 8 * s2, 1); }
+      for (int d = 0; d < 2; ++d) { ptx::mbar_init(b0 + 16 * S + 8 * d, 1); ptx::mbar_init(b0 + 16 * S + 16 + 8 * d, 4); }
+    }
+    ptx::mbar_fence_init();
+  }
+  const uint32_t tmem_cols = static_cast<uint32_t>(2 * kGroups * p.N1pad);     // 256 or 512: two accumulators per group
+  if (tid < 32) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+  const uint32_t tmem_grp = tmem_base + g * 2 * p.N1pad;
+  const uint32_t idesc = ptx::make_idesc_bf16_f32(128, p.N1pad);
+  const uint32_t b_lbo = p.N1pad * 16;
+  const int nb = (p.K + kTmaSym - 1) / kTmaSym;                  // stages per tile
+  const int ksteps = p.Kpad / 16;                                 // K steps the weight image holds (the rest of A is zero)
+  const int64_t num_tiles = (p.B + 127) >> 7;
+  const int64_t tile_stride = static_cast<int64_t>(gridDim.x) * kGroups;
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kGroups + g;
+  const int64_t my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
+
+  if (is_driver) {
+    const int64_t items = my_tiles * nb;
+    bool ok = true;
+    auto load_item = [&](int64_t it) {            // elected lane: arm the stage's barrier and start its copy
+      const int slot = static_cast<int>(it % S);
+      const int64_t tl = it / nb;
+      const int b = static_cast<int>(it - tl * nb);
+      ptx::mbar_arrive_expect_tx(bar_full + 8 * slot, kTmaStageBytes);
+      tma_load_2d(grp_ring + slot * kTmaStageBytes, &tmap, b * kTmaSym, static_cast<int>((tile0 + tl * tile_stride) * 128), bar_full + 8 * slot);
+    };
+    if (ptx::elect_one())
+      for (int64_t it = 0; it < S - 1 && it < items; ++it) load_item(it);
+    int64_t it = 0;
+    for (int64_t tl = 0; tl < my_tiles && ok; ++tl) {
+      const int d = static_cast<int>(tl & 1);
+      if (tl >= 2 && !ptx::mbar_wait_bounded(bar_dfree + 8 * d, static_cast<uint32_t>((tl >> 1) - 1) & 1u, kMaxWaitMs)) { atomicExch(p.abort_flag, 24); ok = false; break; }
+      for (int b = 0; b < nb && ok; ++b, ++it) {
+        const int slot = static_cast<int>(it % S);
+        if (!ptx::mbar_wait_bounded(bar_full + 8 * slot, static_cast<uint32_t>(it / S) & 1u, kMaxWaitMs)) { atomicExch(p.abort_flag, 25); ok = false; break; }
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < kTmaSym / 16; ++j) {
+            const int kstep = (kTmaSym / 16) * b + j;
+            if (kstep < ksteps)
+              ptx::umma_f16_ss(tmem_grp + d * p.N1pad, make_smem_desc_sw128(grp_ring + slot * kTmaStageBytes + j * 32),
+                               ptx::make_smem_desc16(sbase16, kstep * 2 * b_lbo, b_lbo, kSBO), idesc, (b > 0 || j > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(bar_free + 8 * slot);
+          if (b == nb - 1) ptx::umma_commit(bar_done + 8 * d);
+        }
+        // the stage of item it - 1 (its MMAs were issued one iteration ago) takes item it + S - 1
+        const int64_t nit = it + S - 1;
+        if (nit < items) {
+          if (it >= 1) {
+            const int pslot = static_cast<int>((it - 1) % S);
+            if (!ptx::mbar_wait_bounded(bar_free + 8 * pslot, static_cast<uint32_t>((it - 1) / S) & 1u, kMaxWaitMs)) { atomicExch(p.abort_flag, 26); ok = false; break; }
+          }
+          if (ptx::elect_one()) load_item(nit);
+        }
+      }
+    }
+  } else {
+    const uint32_t tmem_d = tmem_grp + (static_cast<uint32_t>(wq * 32) << 16);
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int d = static_cast<int>(tl & 1);
+      if (!ptx::mbar_wait_bounded(bar_done + 8 * d, static_cast<uint32_t>(tl >> 1) & 1u, kMaxWaitMs)) { atomicExch(p.abort_flag, 27); break; }
+      ptx::tc_fence_after();
+      tile_epilogue(p, l2s, tmem_d + d * p.N1pad, (tile0 + tl * tile_stride) * 128 + r, true);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_dfree + 8 * d);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int ks_tma_smem_bytes(int Kpad, int N1pad) {
+  const int w_bytes = (Kpad / 8) * N1pad * 16;
+  const int l2_floats = N1pad + N1pad * kMaxOut + kMaxOut;
+  const int bar_off = (w_bytes + l2_floats * 4 + 15) & ~15;
+  const int ring_off = (bar_off + 512 + 1023) & ~1023;
+  return ring_off + kGroups * kTmaStages * kTmaStageBytes;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libnvd links only the CUDA runtime)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// returns NVD_ERR_UNSUPPORTED when the rows cannot be described to the copy engine (the caller then uses cp.async)
+int launch_ks_tma(nvd_ctx* ctx, const KsParams& p) {
+  const EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || getenv("NVD_KSTREAM_NO_TMA")) return NVD_ERR_UNSUPPORTED;
+  if (ks_tma_smem_bytes(p.Kpad, p.N1pad) > 227 * 1024) return NVD_ERR_UNSUPPORTED;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.B)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.row_stride) * 2};
+  const cuuint32_t box[2] = {kTmaSym, 128};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p.y), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return NVD_ERR_UNSUPPORTED;
+  const int smem = ks_tma_smem_bytes(p.Kpad, p.N1pad);
+  NVD_CUDA(cudaFuncSetAttribute(mlp_kstream_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (p.B + 127) / 128;
+  const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, (tiles + kGroups - 1) / kGroups));
+  mlp_kstream_tma_kernel<<<grid, kTmaThreads, smem, ctx->stream>>>(p, tmap);
+  NVD_CHECK_LAUNCH();
+  return NVD_OK;
 }
 
 uint16_t f32_to_bf16_rn(float f) {
@@ -462,7 +654,12 @@ int launch_mlp_kstream(nvd_ctx* ctx, const MlpModel& m, const __nv_bfloat16* y, 
   if (a % 4 != 0 || sb % 4 != 0) { set_error("bf16 rows must be 4-byte aligned (base and stride)"); return NVD_ERR_INVALID; }
   // a piece must not straddle the end of the row's valid data unevenly: K * 2 bytes is a multiple of 4 for even K only
   if ((p.K & 1) != 0) { set_error("K-streamed tensor-core path needs an even input width (got %d)", p.K); return NVD_ERR_UNSUPPORTED; }
-  if (a % 16 == 0 && sb % 16 == 0) { p.cp_bytes = 16; return launch_ks<KS_STAGED, 16>(ctx, p); }
+  if (a % 16 == 0 && sb % 16 == 0) {
+    const int st = launch_ks_tma(ctx, p);              // 16-byte aligned rows: the copy engine streams them
+    if (st != NVD_ERR_UNSUPPORTED) return st;
+    p.cp_bytes = 16;
+    return launch_ks<KS_STAGED, 16>(ctx, p);
+  }
   if (a % 8 == 0 && sb % 8 == 0) { p.cp_bytes = 8; return launch_ks<KS_STAGED, 8>(ctx, p); }
   p.cp_bytes = 4;
   return launch_ks<KS_STAGED, 4>(ctx, p);

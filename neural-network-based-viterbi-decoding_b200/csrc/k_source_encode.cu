@@ -69,8 +69,12 @@ __global__ void __launch_bounds__(256) source_philox_kernel(uint64_t seed, int L
   const int64_t f = t / nblk;
   const int blk = static_cast<int>(t - f * nblk);
   const uint4 x = frame_words(seed, frame0 + f, blk, kStreamInfo);
-  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
   uint8_t* row = out + f * S;
+  if ((S & 15) == 0 && 128 * (blk + 1) <= L && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    reinterpret_cast<uint4*>(row)[blk] = x;          // a whole block inside 16-byte aligned rows: one vector store
+    return;
+  }
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int byte = 16 * blk + k;

@@ -35,3 +35,15 @@ with mc.Simulator(0) as sim:
     sim.record(e1); sim.sync()
     ms = sim.elapsed_ms(e0, e1) / reps
     print(f"kstream fused : {ms:.4f} ms for {F} frames  {F / ms / 1e3:.1f} Mframes/s  {F * 1036 / ms / 1e6:.1f} Gnormals/s")
+    # staged Monte-Carlo step: K2 writes rows padded to 1040 symbols, the K-streamed kernel takes them by TMA
+    Fs = 1 << 19
+    sim.set_stage_timing(True)
+    cs = sim.zeros(32)
+    for _ in range(2):
+        sim.run_bitwise_async(h, 512, [2.0], Fs, cs, 0, mode="staged", trunc=True)
+    ms = sim.stage_ms()
+    sim.set_stage_timing(False)
+    algb = {"source": 64 + 64 + 65, "encode": 65 + 130, "channel": 130 + 2072, "decode": 2072 + 1, "count": 1 + 1}
+    for k, v in ms.items():
+        v /= (Fs + (1 << 18) - 1) // (1 << 18)
+        print(f"staged MC {k:8s} {v:8.4f} ms per 2^18 frames  {algb[k] * (1 << 18) / v / 1e6:8.1f} GB/s")
