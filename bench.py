@@ -9,11 +9,15 @@ decoded information Gbit/s of the (133,171) K=7 code + FNN decoder (14-128-64-32
 A "step" is one pass of the whole hot path over 2^24 frames at one SNR point (2 dB).
   value  : whole-job info Gbit/s of the fused persistent tcgen05 pipeline (no per-frame HBM input:
            frames are a pure function of seed / SNR index / global frame index), CUDA events on the
-           library's stream, max over ranks, one all-reduce of the counters at the end.
+           library's stream, max over ranks; the counters' ncclAllReduce is issued by the library on
+           the same stream behind the last launch and is inside the timed region.
   e2e    : same metric through the host-buffer C-ABI call nvd_mc_run_host: info words start in
            pinned HOST memory, decisions + counters end in host memory, copies inside the region.
   --impl reference : the CPU oracle port of the reference path (numpy noise + torch-CPU fp32 MLP,
            all host threads) on a bounded sample per step; rank 0 only.
+  extra legs (skipped with --no-legs): `sustained` (>= 3 s of back-to-back launches with clocks and power),
+           `deep_ber` (configs[4], nvd_mc_sweep), `bitwise` + `mixed_snr_sweep` (configs[2]), `rnn_viterbi` (configs[3]),
+           `seq_predict`, `decode_host` (the reference's own decode surface on host arrays).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
