@@ -1064,16 +1064,22 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
   NVD_CUDA(cudaMemsetAsync(ctx->slice_done, 0, HostStepSlices::kMax * sizeof(uint32_t), ctx->stream));
   NVD_CUDA(cudaEventRecord(ctx->slice_ev[0], ctx->stream));          // flags cleared (and earlier work done) before
   NVD_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->slice_ev[0], 0));  // the first slice may land
-  // the copies are queued BEFORE the kernel that waits for them: a tool that makes launches synchronous must not be
-  // able to park the host inside the launch with the copies still unissued
-  for (int s = 0; s < sl.n_in; ++s) {
-    const int64_t off = s ? sl.in_end[s - 1] : 0, n = sl.in_end[s] - off;
+  // Order of the host calls: the first input slice's copies, THEN the launch, then the remaining slices.  The launch
+  // needs ~5 us of host time and the kernel ~10 us of set-up before its first flag wait, both of which now overlap the
+  // queueing of the other sixteen copies (~50 us of API calls that used to sit in front of the launch).  Every
+  // in-kernel wait for a slice is wall-clock bounded, and under a CUDA tools injection (launches may be made
+  // synchronous there) the sliced form runs instead (streaming_default()).
+  auto queue_slice = [&](int s2) -> int {
+    const int64_t off = s2 ? sl.in_end[s2 - 1] : 0, n = sl.in_end[s2] - off;
     NVD_CUDA(cudaMemcpyAsync(d_info + off, info_host + off, n, cudaMemcpyHostToDevice, ctx->copy_in));
-    NVD_CUDA(cudaMemcpyAsync(ctx->slice_flags + s, ctx->slice_ones, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in));
-  }
+    NVD_CUDA(cudaMemcpyAsync(ctx->slice_flags + s2, ctx->slice_ones, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in));
+    return NVD_OK;
+  };
+  NVD_TRY(queue_slice(0));
   NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, cfg->frames,
                               ctx->counters_scratch, d_info, d_pred, ctx->slice_flags, &sl,
                               pred_host ? ctx->slice_done : nullptr, ctx->done_flags_dev));
+  for (int s2 = 1; s2 < sl.n_in; ++s2) NVD_TRY(queue_slice(s2));
   NVD_CUDA(queue_tail_copy(ctx));
   int next = 0;
   const bool trace = getenv("NVD_HOST_STEP_TRACE") != nullptr;      // diagnostics: host-side timeline of this call

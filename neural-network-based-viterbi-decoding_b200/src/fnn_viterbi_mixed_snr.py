@@ -136,10 +136,26 @@ def initialize_weights(config: MixedSNRDecoderConfig) -> Tuple[Dict, Dict]:
     return _fv.initialize_weights(config)
 
 
-def multilayer_perceptron_with_dropout(x, weights: Dict, biases: Dict, keep_prob: float) -> np.ndarray:
-    """Inference-time value of the dropout twin (:596-627): with keep_prob = 1 it equals
-    multilayer_perceptron; dropout itself only exists inside training (nvd.training)."""
-    return multilayer_perceptron(x, weights, biases)
+def multilayer_perceptron_with_dropout(x, weights: Dict, biases: Dict, keep_prob: float, rng=None) -> np.ndarray:
+    """The dropout twin (:596-627): tanh layers with tf.nn.dropout(keep_prob) after each of the three hidden layers.
+    keep_prob = 1 (inference) is multilayer_perceptron itself; for keep_prob < 1 every layer still runs on the GPU
+    (one single-layer model each, cached) and the inverted-dropout mask — keep with probability keep_prob, scale
+    the kept units by 1 / keep_prob, as tf.nn.dropout does — is drawn on the host from `rng` (numpy Generator)."""
+    keep_prob = float(keep_prob)
+    if keep_prob >= 1.0:
+        return multilayer_perceptron(x, weights, biases)
+    if not 0.0 < keep_prob < 1.0:
+        raise ValueError("keep_prob must be in (0, 1]")
+    rng = rng if rng is not None else np.random.default_rng()
+    from nvd import _lib
+    sim = runtime.get_sim()
+    h = np.asarray(x, dtype=np.float32)
+    for wk, bk, last in (("h1", "b1", False), ("h2", "b2", False), ("h3", "b3", False), ("out", "out", True)):
+        layer = _weights.MlpModel([np.asarray(weights[wk], np.float32)], [np.asarray(biases[bk], np.float32)], [_lib.ACT_TANH])
+        _, h = sim.decode(runtime.cached_mlp(layer), h, "fp32")
+        if not last:
+            h = h * (rng.random(h.shape) < keep_prob).astype(np.float32) / np.float32(keep_prob)
+    return h
 
 
 def calculate_ber(predictions: np.ndarray, labels: np.ndarray, block_length: int) -> float:

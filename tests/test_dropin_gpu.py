@@ -154,3 +154,22 @@ log_to_console: false
     assert (tmp_path / "results" / "training_history.json").exists() and (tmp_path / "models" / "final_model.npz").exists()
     assert len(t.metrics_tracker.history) == 2 and 0 <= t.final_metrics.ber <= 1
     assert t.checkpoint_manager.get_best_checkpoint("ber") is not None
+
+
+def test_dropout_twin_runs_on_the_gpu():
+    """multilayer_perceptron_with_dropout (/root/reference/src/fnn_viterbi_mixed_snr.py:596-627): keep_prob = 1 equals the
+    plain graph; keep_prob < 1 applies inverted dropout after each hidden layer (reproducible from the generator)."""
+    import fnn_viterbi_mixed_snr as fm
+    from oracle import mlp as omlp
+    cfg = fm.MixedSNRDecoderConfig()
+    W, b = fm.initialize_weights(cfg)
+    x = np.random.default_rng(0).standard_normal((300, 14)).astype(np.float32)
+    assert np.array_equal(fm.multilayer_perceptron_with_dropout(x, W, b, 1.0), fm.multilayer_perceptron(x, W, b))
+    a = fm.multilayer_perceptron_with_dropout(x, W, b, 0.5, rng=np.random.default_rng(3))
+    rng = np.random.default_rng(3)
+    h = x
+    for wk, bk, last in (("h1", "b1", False), ("h2", "b2", False), ("h3", "b3", False), ("out", "out", True)):
+        h = np.tanh(h.astype(np.float64) @ W[wk] + b[bk]).astype(np.float32)
+        if not last:
+            h = h * (rng.random(h.shape) < 0.5).astype(np.float32) / np.float32(0.5)
+    assert np.abs(a - h).max() <= 1e-5
