@@ -54,11 +54,14 @@ def test_state_prefix_and_bit_counters(sim):
 
 @pytest.mark.parametrize("dims,acts,B", [([1036, 30, 2], [2, 2], 1), ([1036, 30, 2], [2, 2], 5000), ([1040, 30, 2], [2, 2], 129),
                                          ([1038, 30, 2], [2, 2], 257), ([100, 64, 8], [1, 0], 127), ([48, 16, 2], [1, 1], 1000),
-                                         ([1200, 20, 3], [2, 1], 700)])
+                                         ([1200, 20, 3], [2, 1], 700), ([104, 64, 8], [1, 2], 3000), ([1040, 30, 2], [2, 2], 1),
+                                         ([64, 8, 2], [0, 0], 148 * 4 * 128 * 2 + 5)])
 def test_kstream_tensor_core_matches_oracle(sim, dims, acts, B):
     """bf16 rows x bf16 W1 on tcgen05 with fp32 accumulation, the tail in fp32: against the fp64 oracle on the same
     bf16-rounded inputs within 2e-2 of the output scale, and tighter against the oracle with W1 rounded to bf16.
-    Row strides of 2072 / 2080 / 2076 bytes take the 8- / 16- / 4-byte copy paths."""
+    Row strides of 2072 / 2076 bytes take the 8- / 4-byte cp.async paths, 16-byte aligned strides (1040, 104, 64, 48
+    symbols) the TMA path — incl. N1 = 64 (two 64-column accumulators per group), a single row, a single-stage K and
+    more tiles than two rounds of the persistent grid."""
     from nvd import montecarlo as mc
     m = _model(dims, acts, seed=sum(dims))
     h = sim.load_mlp(m)
