@@ -212,10 +212,14 @@ def main():
     sim.allreduce_counters(counters, 4)                 # warm the communicator's first-use set-up
     sim.sync()
     counters = sim.zeros(32)
+    align = sim.zeros(32)
     dist.barrier()
     sim.sync()
     e0, e1, e2 = sim.event(), sim.event(), sim.event()
     sampler.active = True
+    # ranks leave the host barrier tens of microseconds apart; one more (tiny) all-reduce on the library's stream
+    # makes every rank's stream pass the same point together, so the regions start aligned on the DEVICE
+    sim.allreduce_counters(align, 4)
     sim.record(e0)
     for s in range(args.steps):
         sim.run_async(h, "133171", L, [SNR_DB], frames, counters, frame0 + s * world * frames, mode="fused")
