@@ -615,6 +615,7 @@ void fill_common(KsParams& p, nvd_ctx* ctx, const MlpModel& m) {
 
 bool kstream_supported(const MlpModel& m) {
   if (m.n_layers != 2 || m.dims[1] > 64 || m.dims[2] > kMaxOut || m.dims[0] < 16) return false;
+  if (m.dims[0] & 1) return false;                      // bf16 rows must be 4-byte aligned: even input width
   const int Kpad = (m.dims[0] + kBatchSym - 1) / kBatchSym * kBatchSym;
   const int N1pad = m.dims[1] <= 32 ? 32 : 64;
   return ks_smem_bytes(Kpad, N1pad, kStagesStaged) <= 227 * 1024;

@@ -92,6 +92,7 @@ def test_kstream_empty_and_unsupported(sim):
     h = sim.load_mlp(m)
     sim.mlp_forward(h, sim.zeros(64), "bf16", 0, 2, "bf16")                 # empty batch is a no-op
     h2 = sim.load_mlp(_model([1037, 30, 2], [2, 2], seed=2))                 # odd width: rows are not 4-byte aligned
+    assert not sim.mlp_tc_supported(h2)
     with pytest.raises(NvdError):
         sim.mlp_forward(h2, sim.zeros(1037 * 2 * 4), "bf16", 4, 2, "bf16")
     h3 = sim.load_mlp(_model([1036, 100, 2], [2, 2], seed=3))                # first layer wider than 64, K > 511
