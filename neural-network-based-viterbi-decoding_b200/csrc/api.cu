@@ -1022,7 +1022,9 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
   {
     int64_t done = 0;
     while (done < frames && sl.n_in < HostStepSlices::kMax) {
-      int64_t n = (4 + done / wave / 2) * wave;
+      static const int64_t div = [] { const char* e = getenv("NVD_HOST_SLICE_DIV"); const int v = e ? atoi(e) : 0; return static_cast<int64_t>(v >= 1 ? v : 2); }();
+      static const int64_t first = [] { const char* e = getenv("NVD_HOST_SLICE_FIRST"); const int v = e ? atoi(e) : 0; return static_cast<int64_t>(v >= 1 ? v : 4); }();
+      int64_t n = (first + done / wave / div) * wave;
       if (sl.n_in == HostStepSlices::kMax - 1 || done + n > frames) n = frames - done;
       done += n;
       sl.in_end[sl.n_in++] = done;
