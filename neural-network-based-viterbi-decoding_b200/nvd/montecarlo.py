@@ -444,6 +444,22 @@ class Simulator:
             self.free(b)
         return out
 
+    def host_step(self, h, code, L, snr_db: float, info_host: np.ndarray, pred_host=None, frame0=0, precision="bf16",
+                  snr_idx=0, mode="fused"):
+        """A prepared end-to-end step: the configuration struct and the ctypes arguments are built ONCE; calling the
+        returned function is nothing but the C-ABI call nvd_mc_run_host (counters come back in the returned array,
+        overwritten by every call)."""
+        cfg = self._mc_config(h, code, L, precision, mode, "bf16" if precision == "bf16" else "f32", frame0, info_host.shape[0])
+        counters = np.zeros(4, dtype=np.uint64)
+        args = (self.ctx, C.byref(cfg), C.c_float(float(snr_db)), C.c_int(int(snr_idx)), C.c_void_p(info_host.ctypes.data),
+                C.c_void_p(pred_host.ctypes.data) if pred_host is not None else None, C.c_void_p(counters.ctypes.data))
+        fn = self.lib.nvd_mc_run_host
+
+        def step(_keep=(cfg, info_host, pred_host)):
+            check(fn(*args))
+            return counters
+        return step
+
     def stage_ms(self):
         ms = (C.c_float * 5)()
         check(self.lib.nvd_mc_stage_ms(self.ctx, ms))
