@@ -1077,11 +1077,14 @@ static int mc_run_host_streaming(nvd_ctx* ctx, const nvd_mc_config* cfg, MlpMode
     NVD_CUDA(cudaMemcpyAsync(ctx->slice_flags + s2, ctx->slice_ones, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_in));
     return NVD_OK;
   };
-  NVD_TRY(queue_slice(0));
+  // (streaming forced by NVD_HOST_STEP under a tools injection, e.g. `ncu --replay-mode application`: a profiler may
+  // hold the host inside the launch until the kernel has finished, so there every copy is queued first)
+  const int before_launch = streaming_default() ? 1 : sl.n_in;
+  for (int s2 = 0; s2 < before_launch; ++s2) NVD_TRY(queue_slice(s2));
   NVD_TRY(launch_mlp_tc_fused(ctx, *m, cfg->code, cfg->L, sigma_of_db(snr_db), snr_idx, cfg->frame0, cfg->frames,
                               ctx->counters_scratch, d_info, d_pred, ctx->slice_flags, &sl,
                               pred_host ? ctx->slice_done : nullptr, ctx->done_flags_dev));
-  for (int s2 = 1; s2 < sl.n_in; ++s2) NVD_TRY(queue_slice(s2));
+  for (int s2 = before_launch; s2 < sl.n_in; ++s2) NVD_TRY(queue_slice(s2));
   NVD_CUDA(queue_tail_copy(ctx));
   int next = 0;
   const bool trace = getenv("NVD_HOST_STEP_TRACE") != nullptr;      // diagnostics: host-side timeline of this call
