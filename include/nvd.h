@@ -121,6 +121,9 @@ int nvd_mlp_free(nvd_ctx* ctx, int model);
 int nvd_mlp_forward(nvd_ctx* ctx, int model, const void* y, int y_dtype, int64_t B, int precision,
                     float* soft_out, void* hard_out, int hard_bytes);
 int nvd_mlp_tc_supported(nvd_ctx* ctx, int model, int* supported);
+/* device address of a loaded model's fp32 parameters: layer's weights [dims[l], dims[l+1]] (weight != 0) or biases
+ * [dims[l+1]] — what a training step updates in place (nvd_train_step) and a caller may read with nvd_memcpy_d2h */
+int nvd_mlp_param(nvd_ctx* ctx, int model, int layer, int weight, void** dptr);
 /* Sliding-window decode (src/fnn_viterbi_seq_predict.py:293-336 get_single_instance + the forward of :343-414):
  * window i = stream[i * stride, i * stride + dims[0]) of one long symbol stream in device memory
  * (stream_dtype NVD_F32 / NVD_BF16 / NVD_I32_TRUNC), i < n_windows; soft_out [n_windows, n_out] fp32 or NULL,
@@ -254,6 +257,27 @@ int nvd_count_row_errors(nvd_ctx* ctx, const uint8_t* pred_packed, int pred_stri
 /* the six start-state bits in front of every packed frame (encode_133171_with_state, src/fnn_viterbi_bitwise.py:162-163):
  * out [B, ceil((L + n_state_bits) / 8)] */
 int nvd_prepend_state(nvd_ctx* ctx, const uint8_t* info_packed, int L, int state, int n_state_bits, int64_t B, uint8_t* out);
+
+/* ---- training step of the feed-forward decoders (the step before the path) -----------------------
+ * replaces the TensorFlow-1.x session loops: forward, cost = mean softmax cross-entropy on the activated outputs (or mean
+ * sigmoid cross-entropy, src/fnn_viterbi_bitwise.py:439-448) + beta * sum over the masked layers of sum(w^2)/2
+ * (src/fnn_viterbi.py:549-559), backward, tf.train.AdamOptimizer (:562-564; TensorFlow's update
+ * lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t), w -= lr_t m / (sqrt(v) + epsilon)).  fp32 throughout.  The model's device
+ * parameters are updated in place by every step; nvd_train_end copies them to the host arrays (may be NULL), rebuilds the
+ * model's tensor-core images from them and releases the trainer.  x_dev [B, dims[0]] fp32, y_dev [B, n_out] fp32 targets
+ * (one-hot rows), B <= max_batch.  cost_host (may be NULL; non-NULL synchronises) receives the step's cost before the update. */
+enum { NVD_LOSS_SOFTMAX_CE = 0, NVD_LOSS_SIGMOID_CE = 1 };
+typedef struct {
+  int32_t struct_bytes;     /* = sizeof(nvd_train_config) */
+  int32_t loss;             /* NVD_LOSS_* */
+  float learning_rate;
+  float beta;               /* L2 weight (beta_regularization) */
+  uint32_t l2_layer_mask;   /* bit l: layer l's weights are in the L2 term */
+  float beta1, beta2, epsilon;   /* Adam: 0.9, 0.999, 1e-8 are TensorFlow's defaults */
+} nvd_train_config;
+int nvd_train_begin(nvd_ctx* ctx, int model, const nvd_train_config* cfg, int64_t max_batch, int* trainer);
+int nvd_train_step(nvd_ctx* ctx, int trainer, const float* x_dev, const float* y_dev, int64_t B, float* cost_host);
+int nvd_train_end(nvd_ctx* ctx, int trainer, float* const* W_host, float* const* b_host);
 
 /* ---- multi-GPU exchange step ------------------------------------------------------------------
  * The reference is single-process; the path shards by global frame range, one context (process or

@@ -182,6 +182,7 @@ int nvd_ctx_destroy(nvd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   comm_release(ctx);
+  trainers_release(ctx);
   for (auto& m : ctx->mlps) {
     for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m.W[l]); cudaFree(m.b[l]); }
     cudaFree(m.tc_image);
@@ -425,6 +426,15 @@ int nvd_mlp_free(nvd_ctx* ctx, int model) {
   for (int l = 0; l < kMaxLayers; ++l) { cudaFree(m->wide_image[l]); m->wide_image[l] = nullptr; }
   m->wide = false;
   m->live = false;
+  return NVD_OK;
+}
+
+int nvd_mlp_param(nvd_ctx* ctx, int model, int layer, int weight, void** dptr) {
+  NVD_REQUIRE(ctx && dptr, "null argument");
+  MlpModel* m;
+  NVD_TRY(get_mlp(ctx, model, &m));
+  NVD_REQUIRE(layer >= 0 && layer < m->n_layers, "layer %d out of range", layer);
+  *dptr = weight ? static_cast<void*>(m->W[layer]) : static_cast<void*>(m->b[layer]);
   return NVD_OK;
 }
 

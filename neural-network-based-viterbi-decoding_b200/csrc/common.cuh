@@ -79,6 +79,24 @@ struct LstmModel {
 
 }  // namespace nvd
 
+// state of one nvd_train_begin .. nvd_train_end run (k_train.cu): activations of a step, gradients, Adam moments
+struct nvd_trainer {
+  int model = -1;
+  nvd_train_config cfg{};
+  int64_t max_batch = 0;
+  int64_t step = 0;
+  float* act[nvd::kMaxLayers + 1] = {nullptr};   // act[l + 1] = activation of layer l, [max_batch, dims[l + 1]]
+  float* delta[2] = {nullptr, nullptr};          // ping-pong d(activation) buffers, widest layer
+  float* gW[nvd::kMaxLayers] = {nullptr};
+  float* gb[nvd::kMaxLayers] = {nullptr};
+  float* mW[nvd::kMaxLayers] = {nullptr};
+  float* vW[nvd::kMaxLayers] = {nullptr};
+  float* mb[nvd::kMaxLayers] = {nullptr};
+  float* vb[nvd::kMaxLayers] = {nullptr};
+  float* cost = nullptr;                         // device scalar
+  bool live = false;
+};
+
 struct nvd_ctx {
   int device = 0;
   int sm_count = 0;
@@ -88,6 +106,7 @@ struct nvd_ctx {
   cudaStream_t stream = nullptr;
   std::vector<nvd::MlpModel> mlps;
   std::vector<nvd::LstmModel> lstms;
+  std::vector<nvd_trainer> trainers;
   // device-side abort flag written by kernels whose bounded waits expire
   int* abort_flag = nullptr;       // device
   int* abort_flag_host = nullptr;  // pinned mirror
@@ -124,6 +143,7 @@ int ensure_scratch(nvd_ctx* ctx, size_t bytes);
 // comm.cu: in-place sum of n uint64 device values over the context's communicator, on ctx->stream (no-op without one)
 int comm_allreduce_u64(nvd_ctx* ctx, uint64_t* values_dev, size_t n);
 void comm_release(nvd_ctx* ctx);
+void trainers_release(nvd_ctx* ctx);            // k_train.cu
 
 // ---- kernel launchers (each validates nothing; the API layer does) -----------------------
 int launch_source(nvd_ctx* ctx, int L, uint64_t frame0, int64_t B, uint8_t* info_packed);

@@ -38,6 +38,14 @@ class McConfig(C.Structure):
                 ("frame0", C.c_uint64), ("frames", C.c_uint64)]
 
 
+class TrainConfig(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("loss", C.c_int32), ("learning_rate", C.c_float), ("beta", C.c_float),
+                ("l2_layer_mask", C.c_uint32), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float)]
+
+
+LOSSES = {"softmax_ce": 0, "sigmoid_ce": 1}
+
+
 class McBitwiseConfig(C.Structure):
     _fields_ = [("struct_bytes", C.c_int32), ("model", C.c_int32), ("code", C.c_int32), ("L", C.c_int32),
                 ("n_state_bits", C.c_int32), ("state", C.c_int32), ("bit_position", C.c_int32), ("precision", C.c_int32),
@@ -78,6 +86,7 @@ _PROTOS = {
     "nvd_mlp_free": ([_vp, _i], _i),
     "nvd_mlp_forward": ([_vp, _i, _vp, _i, _i64, _i, _vp, _vp, _i], _i),
     "nvd_mlp_tc_supported": ([_vp, _i, C.POINTER(_i)], _i),
+    "nvd_mlp_param": ([_vp, _i, _i, _i, C.POINTER(_vp)], _i),
     "nvd_window_decode": ([_vp, _i, _vp, _i, _i64, _i64, _i64, _i, _vp, _vp, _i], _i),
     "nvd_tc_tanh_model": ([C.POINTER(_i), C.POINTER(_f), C.POINTER(_f)], _i),
     "nvd_mlp_decode_host": ([_vp, _i, _vp, _i64, _i, _vp, _vp], _i),
@@ -94,6 +103,9 @@ _PROTOS = {
     "nvd_count_bit_errors": ([_vp, _vp, _vp, _i, _i, _i64, _vp], _i),
     "nvd_count_row_errors": ([_vp, _vp, _i, _vp, _i, _i, _i64, _vp], _i),
     "nvd_prepend_state": ([_vp, _vp, _i, _i, _i, _i64, _vp], _i),
+    "nvd_train_begin": ([_vp, _i, C.POINTER(TrainConfig), _i64, C.POINTER(_i)], _i),
+    "nvd_train_step": ([_vp, _i, _vp, _vp, _i64, C.POINTER(_f)], _i),
+    "nvd_train_end": ([_vp, _i, C.POINTER(_vp), C.POINTER(_vp)], _i),
     "nvd_comm_unique_id": ([_vp], _i),
     "nvd_comm_init": ([_vp, _i, _i, _vp], _i),
     "nvd_comm_destroy": ([_vp], _i),

@@ -16,7 +16,95 @@ def _torch():
 
 
 def train_mlp(model, x, y_onehot, *, acts, loss="softmax_ce", beta=0.0, l2_layers=(0, 1, 2), lr=1e-4, epochs=1,
-              batch_size=256, dropout_keep=None, display_step=1, log=print, epoch_callback=None):
+              batch_size=256, dropout_keep=None, display_step=1, log=print, epoch_callback=None, backend=None):
+    """Train `model` in place; returns the per-epoch costs.  backend "native" (default when no dropout is asked for):
+    libnvd's own training step, nvd_train_begin / nvd_train_step / nvd_train_end (csrc/k_train.cu) — forward, cost,
+    backward, L2 and TensorFlow's Adam as CUDA kernels on the process-wide Simulator; backend "torch": the autograd
+    restatement below (needed for dropout; CPU-capable, used by the tools that build weight fixtures)."""
+    if backend is None:
+        backend = "torch" if dropout_keep is not None else "native"
+    if backend == "native":
+        if dropout_keep is not None:
+            raise ValueError("the native training step has no dropout; use backend='torch'")
+        return train_mlp_native(model, x, y_onehot, acts=acts, loss=loss, beta=beta, l2_layers=l2_layers, lr=lr, epochs=epochs,
+                                batch_size=batch_size, display_step=display_step, log=log, epoch_callback=epoch_callback)
+    return train_mlp_torch(model, x, y_onehot, acts=acts, loss=loss, beta=beta, l2_layers=l2_layers, lr=lr, epochs=epochs,
+                           batch_size=batch_size, dropout_keep=dropout_keep, display_step=display_step, log=log,
+                           epoch_callback=epoch_callback)
+
+
+def train_mlp_native(model, x, y_onehot, *, acts, loss="softmax_ce", beta=0.0, l2_layers=(0, 1, 2), lr=1e-4, epochs=1,
+                     batch_size=256, display_step=1, log=print, epoch_callback=None, sim=None):
+    """Mini-batch training on the GPU through the C ABI, in the reference's fixed batch order (fnn_viterbi.py:579-585).
+    The whole training set and its one-hot targets are uploaded once; every step is three GEMMs per layer plus
+    elementwise kernels; the cost of every step is read back (4 bytes) for the per-epoch average the reference prints."""
+    import ctypes as C
+
+    from . import _lib, runtime
+    from .weights import MlpModel
+    sim = sim or runtime.get_sim()
+    m = MlpModel([np.ascontiguousarray(W, np.float32) for W in model.Ws], [np.ascontiguousarray(b, np.float32) for b in model.bs],
+                 [int(a) for a in acts])
+    h = sim.load_mlp(m)
+    cfg = _lib.TrainConfig()
+    cfg.struct_bytes = C.sizeof(_lib.TrainConfig)
+    cfg.loss = _lib.LOSSES[loss]
+    cfg.learning_rate, cfg.beta = float(lr), float(beta)
+    cfg.l2_layer_mask = sum(1 << int(l) for l in l2_layers if int(l) < len(m.Ws))
+    cfg.beta1, cfg.beta2, cfg.epsilon = 0.9, 0.999, 1e-8
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y_onehot, dtype=np.float32)
+    n, n_in, n_out = x.shape[0], x.shape[1], y.shape[1]
+    total_batch = int(n / batch_size)
+    tr = C.c_int(-1)
+    _lib.check(sim.lib.nvd_train_begin(sim.ctx, h, C.byref(cfg), batch_size, C.byref(tr)))
+    d_x, d_y = sim.to_device(x[: total_batch * batch_size]), sim.to_device(y[: total_batch * batch_size])
+    costs, cost = [], C.c_float(0.0)
+
+    def read_back():
+        Wp = (C.c_void_p * len(m.Ws))(*[W.ctypes.data for W in m.Ws])
+        bp = (C.c_void_p * len(m.bs))(*[b.ctypes.data for b in m.bs])
+        return Wp, bp
+
+    try:
+        for epoch in range(epochs):
+            avg = 0.0
+            for i in range(total_batch):
+                _lib.check(sim.lib.nvd_train_step(sim.ctx, tr.value, d_x.ptr + i * batch_size * n_in * 4,
+                                                  d_y.ptr + i * batch_size * n_out * 4, batch_size, C.byref(cost)))
+                avg += cost.value / max(total_batch, 1)
+            costs.append(avg)
+            if display_step and epoch % display_step == 0:
+                log(f"Epoch: {epoch + 1:04d} | cost = {avg:.9f}")
+            if epoch_callback is not None:
+                for l in range(len(m.Ws)):      # the callback evaluates / checkpoints the current parameters
+                    _lib.check(sim.lib.nvd_memcpy_d2h(sim.ctx, m.Ws[l].ctypes.data, _device_param(sim, h, l, True), m.Ws[l].nbytes))
+                    _lib.check(sim.lib.nvd_memcpy_d2h(sim.ctx, m.bs[l].ctypes.data, _device_param(sim, h, l, False), m.bs[l].nbytes))
+                sim.sync()
+                model.Ws, model.bs = [W.copy() for W in m.Ws], [b.copy() for b in m.bs]
+                if epoch_callback(epoch, avg, model):
+                    break
+    finally:
+        Wp, bp = read_back()
+        _lib.check(sim.lib.nvd_train_end(sim.ctx, tr.value, Wp, bp))
+        for b in (d_x, d_y):
+            sim.free(b)
+        _lib.check(sim.lib.nvd_mlp_free(sim.ctx, h))
+    model.Ws, model.bs = [W.copy() for W in m.Ws], [b.copy() for b in m.bs]
+    return costs
+
+
+def _device_param(sim, h, layer, weight):
+    import ctypes as C
+
+    from . import _lib
+    p = C.c_void_p()
+    _lib.check(sim.lib.nvd_mlp_param(sim.ctx, h, layer, int(weight), C.byref(p)))
+    return p
+
+
+def train_mlp_torch(model, x, y_onehot, *, acts, loss="softmax_ce", beta=0.0, l2_layers=(0, 1, 2), lr=1e-4, epochs=1,
+                    batch_size=256, dropout_keep=None, display_step=1, log=print, epoch_callback=None):
     """Mini-batch Adam over (x, y_onehot) in the reference's fixed batch order (no shuffling:
     fnn_viterbi.py:579-585).  cost = mean CE(out, y) + beta * sum_l l2_loss(W_l) with
     tf.nn.l2_loss(W) = sum(W^2)/2.  Updates `model` in place and returns the per-epoch costs.

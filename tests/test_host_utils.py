@@ -51,7 +51,7 @@ def test_training_keeps_one_optimizer_across_epochs():
     y = np.eye(128, dtype=np.float32)[rng.integers(0, 128, 512)]
     def fresh():
         return weights.init_mlp([14, 128, 64, 32, 128], ["tanh"] * 4, seed=5)
-    kw = dict(acts=[1, 1, 1, 1], loss="softmax_ce", beta=1e-3, lr=1e-3, batch_size=64, display_step=0)
+    kw = dict(acts=[1, 1, 1, 1], loss="softmax_ce", beta=1e-3, lr=1e-3, batch_size=64, display_step=0, backend="torch")
     a, b, c = fresh(), fresh(), fresh()
     torch.manual_seed(0)
     costs_a = training.train_mlp(a, x, y, epochs=3, **kw)
