@@ -1,10 +1,10 @@
 """Training loops of the drop-in modules (the step BEFORE the hot path).
 
 The reference trains inside a TensorFlow-1.x session (/root/reference/src/fnn_viterbi.py:549-603,
-fnn_viterbi_mixed_snr.py:722-785, fnn_viterbi_bitwise.py:439-497, rnn_viterbi.py:311-316).  Here the
-same objectives are restated with torch autograd (plumbing: CUDA when available, else CPU); the
-trained parameters are handed to libnvd, whose kernels do every forward pass that produces a
-reported decision or BER.  Training is not part of the accelerated path and is kept simple."""
+fnn_viterbi_mixed_snr.py:722-785, fnn_viterbi_bitwise.py:439-497, rnn_viterbi.py:311-316).  The feed-forward
+decoders train through libnvd's own training step (nvd_train_*, csrc/k_train.cu); the dropout variant and the
+LSTM's MSE objective are restated with torch autograd (plumbing: CUDA when available, else CPU).  Either way the
+trained parameters are handed to libnvd, whose kernels do every forward pass that produces a reported decision or BER."""
 from __future__ import annotations
 
 import numpy as np
