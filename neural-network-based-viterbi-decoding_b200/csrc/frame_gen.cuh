@@ -85,7 +85,11 @@ constexpr int kNormalsPerBlock = 6;
 
 // radius / angle fields of pair i (0..2) of a block
 __device__ __forceinline__ float bm_log2_u1(uint32_t xi) {          // lg2((r_bits + 0.5) * 2^-27)
-  return __log2f(fmaf(__uint2float_rn(xi >> 5), 7.450580596923828e-9f, 3.725290298461914e-9f));
+  // the argument is >= 2^-28, never subnormal: the .ftz form is the same function here without the four instructions
+  // of subnormal scaling that __log2f wraps around MUFU.LG2
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaf(__uint2float_rn(xi >> 5), 7.450580596923828e-9f, 3.725290298461914e-9f)));
+  return l;
 }
 template <int I>
 __device__ __forceinline__ float bm_theta(uint32_t xi, uint32_t x3) {   // int32(a_bits << 17) * pi * 2^-31
@@ -121,25 +125,47 @@ __device__ __forceinline__ void noise6(const PhiloxKeys& rk, uint64_t frame, uin
 }
 
 // the 14 normals of an L = 7 frame (blocks 0, 1 and the first pair of block 2): the three Philox chains first, then
-// the seven Box-Muller pairs stage by stage
-__device__ __forceinline__ void noise14(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, float z[14]) {
+// the seven Box-Muller pairs stage by stage.  The three stages are separate functions so that a caller with idle time
+// in three places (the fused decoder's epilogue threads, between a hand-off to the tensor core and its completion)
+// can run one stage in each; noise14 is their composition, so both forms give the same bits.
+struct Noise14Words {
+  uint32_t w[7];   // radius words of the seven pairs (low 5 bits: angle)
+  uint32_t a[3];   // word 3 of the three blocks (angle fields)
+};
+__device__ __forceinline__ void noise14_words(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, Noise14Words& n) {
   const uint4 x0 = frame_words(rk, frame, 0u, stream_word);
   const uint4 x1 = frame_words(rk, frame, 1u, stream_word);
+#ifdef NVD_EXP_TWO_CALLS   // timing experiment only (wrong noise): what a third Philox call costs
+  const uint4 x2 = make_uint4(x0.x ^ x1.y, x0.y ^ x1.z, x0.z ^ x1.w, x0.w ^ x1.x);
+#else
   const uint4 x2 = frame_words(rk, frame, 2u, stream_word);
-  const uint32_t w[7] = {x0.x, x0.y, x0.z, x1.x, x1.y, x1.z, x2.x};
-  float l[7], th[7], r[7];
+#endif
+  n.w[0] = x0.x; n.w[1] = x0.y; n.w[2] = x0.z; n.w[3] = x1.x; n.w[4] = x1.y; n.w[5] = x1.z; n.w[6] = x2.x;
+  n.a[0] = x0.w; n.a[1] = x1.w; n.a[2] = x2.w;
+}
+__device__ __forceinline__ void noise14_polar(const Noise14Words& n, float (&r)[7], float (&th)[7]) {
+  float l[7];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) l[i] = bm_log2_u1(w[i]);
-  th[0] = bm_theta<0>(x0.x, x0.w); th[1] = bm_theta<1>(x0.y, x0.w); th[2] = bm_theta<2>(x0.z, x0.w);
-  th[3] = bm_theta<0>(x1.x, x1.w); th[4] = bm_theta<1>(x1.y, x1.w); th[5] = bm_theta<2>(x1.z, x1.w);
-  th[6] = bm_theta<0>(x2.x, x2.w);
+  for (int i = 0; i < 7; ++i) l[i] = bm_log2_u1(n.w[i]);
+  th[0] = bm_theta<0>(n.w[0], n.a[0]); th[1] = bm_theta<1>(n.w[1], n.a[0]); th[2] = bm_theta<2>(n.w[2], n.a[0]);
+  th[3] = bm_theta<0>(n.w[3], n.a[1]); th[4] = bm_theta<1>(n.w[4], n.a[1]); th[5] = bm_theta<2>(n.w[5], n.a[1]);
+  th[6] = bm_theta<0>(n.w[6], n.a[2]);
 #pragma unroll
   for (int i = 0; i < 7; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);
+}
+__device__ __forceinline__ void noise14_finish(const float (&r)[7], const float (&th)[7], float z[14]) {
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     z[2 * i] = r[i] * __cosf(th[i]);
     z[2 * i + 1] = r[i] * __sinf(th[i]);
   }
+}
+__device__ __forceinline__ void noise14(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, float z[14]) {
+  Noise14Words n;
+  float r[7], th[7];
+  noise14_words(rk, frame, stream_word, n);
+  noise14_polar(n, r, th);
+  noise14_finish(r, th, z);
 }
 
 // ---- encoder on packed words ---------------------------------------------------------------

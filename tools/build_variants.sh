@@ -14,6 +14,6 @@ for V in "$@"; do
 done
 wait
 for V in "$@"; do
-  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/var/libnvd_$V.so build/api.o build/comm.o build/k_mlp_kstream.o build/k_source_encode.o build/k_channel.o build/k_mlp_fp32.o build/k_mlp_wide_tc.o build/var/k_mlp_tc_$V.o build/k_lstm.o build/k_lstm_tc.o build/k_count.o -ldl
+  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/var/libnvd_$V.so build/api.o build/comm.o build/k_mlp_kstream.o build/k_source_encode.o build/k_channel.o build/k_mlp_fp32.o build/k_mlp_wide_tc.o build/var/k_mlp_tc_$V.o build/k_lstm.o build/k_lstm_tc.o build/k_count.o build/k_train.o -ldl
 done
 ls build/var/*.so
