@@ -1,7 +1,7 @@
 // frame_gen.cuh — device functions shared by the staged kernels (K0/K1/K2) and the fused
 // pipeline kernel, so that both produce bit-identical frames:
 //   * Philox4x32-10 counter-based generator (checked word-for-word against oracle/philox.py)
-//   * Box–Muller on MUFU (lg2 / sqrt / sin / cos approximations), six normals per Philox call
+//   * Box–Muller on MUFU (lg2 / sqrt / sin / cos approximations), eight normals per Philox call
 //   * shift-XOR convolutional encoder on time-packed words
 //       encode_133171  /root/reference/src/fnn_viterbi.py:157-217  taps {0,2,3,5,6} / {0,1,2,3,6}
 //       encode_57      /root/reference/src/fnn_viterbi.py:122-154  taps {0,2} / {0,1,2}, g=5 first,
@@ -15,6 +15,7 @@ namespace nvd {
 
 constexpr uint32_t kStreamNoise = 1u;
 constexpr uint32_t kStreamInfo = 2u;
+constexpr uint32_t kStreamNoiseTail = 3u;   // refinement bits of the rare far-tail radii (= kStreamNoise | 2)
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -78,94 +79,122 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
-// One Philox call (128 bits) feeds SIX symbols (oracle/philox.py block_normals): three Box-Muller pairs, pair i
-// taking a 27-bit radius uniform from the top of word i and a 15-bit angle made of the low 5 bits of word i and bits
-// [10i, 10i+10) of word 3.  Four MUFU operations per pair: lg2, sqrt, cos, sin.
-constexpr int kNormalsPerBlock = 6;
+// One Philox call (128 bits) feeds EIGHT symbols 8*block .. 8*block+7 (oracle/philox.py block_normals): four
+// Box-Muller pairs, pair p made of word p alone — a 20-bit radius field k = w >> 12 and a 12-bit angle field
+// a = w & 0xFFF:
+//     u = (k + 0.5) * 2^-20,   theta = a * 2 pi / 4096 - pi,   r = sqrt(-2 ln u),   z = (r cos theta, r sin theta).
+// Twenty bits alone would end the radius at 5.4 sigma on a coarse grid, so the sixteen lowest cells (k < 16, i.e.
+// w < 2^16, probability 1.5e-5 per pair) are refined by 32 more bits, word p of a SECOND Philox call on the stream
+// kStreamNoiseTail made only when a thread meets such a word:  u = (k * 2^32 + t + 0.5) * 2^-52  (radius up to
+// 8.6 sigma, relative cell width <= 6 % everywhere).  The fast path costs four MUFU operations and eleven other
+// instructions per pair; Philox is the dominant cost of every Monte-Carlo kernel, and the same 128 bits fed 4
+// symbols in round 1 and 6 before this form.
+// The symbol is produced as  y = fma(sigma r, cos theta, +-1): sigma is folded into the radius (c_scale below), so
+// there is no separate multiply of r with the trigonometric factor.
+constexpr int kNormalsPerBlock = 8;
+constexpr uint32_t kTailWordLimit = 1u << 16;          // w < 2^16  <=>  radius field k < 16
 
-// radius / angle fields of pair i (0..2) of a block
-__device__ __forceinline__ float bm_log2_u1(uint32_t xi) {          // lg2((r_bits + 0.5) * 2^-27)
-  // the argument is >= 2^-28, never subnormal: the .ftz form is the same function here without the four instructions
-  // of subnormal scaling that __log2f wraps around MUFU.LG2
+__host__ __device__ __forceinline__ float bm_scale(float sigma) { return -1.3862943611198906f * sigma * sigma; }   // -2 ln 2 sigma^2
+__device__ __forceinline__ uint32_t tail_stream_word(uint32_t noise_stream_word) { return noise_stream_word | 2u; }
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  // the arguments here are never subnormal (>= 2^-53): the .ftz form is the same function without the four
+  // instructions of subnormal scaling that __log2f wraps around MUFU.LG2
   float l;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaf(__uint2float_rn(xi >> 5), 7.450580596923828e-9f, 3.725290298461914e-9f)));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
   return l;
 }
-template <int I>
-__device__ __forceinline__ float bm_theta(uint32_t xi, uint32_t x3) {   // int32(a_bits << 17) * pi * 2^-31
-  const uint32_t lo = (I == 0) ? (x3 << 17) : (I == 1) ? (x3 << 7) : (x3 >> 3);
-  uint32_t t;
-  asm("lop3.b32 %0, %1, 0x07FE0000, %2, 0xEA;" : "=r"(t) : "r"(lo), "r"(xi << 27));   // (lo & mask) | (xi << 27)
-  return __int2float_rn(static_cast<int>(t)) * 1.4629180792671596e-9f;                 // pi * 2^-31
+__device__ __forceinline__ float bm_lg2_u(uint32_t w) {                   // lg2((k + 0.5) * 2^-20)
+  return lg2_approx(fmaf(__uint2float_rn(w >> 12), 9.5367431640625e-7f, 4.76837158203125e-7f));
+}
+__device__ __forceinline__ float bm_lg2_u_tail(uint32_t w, uint32_t t) {  // lg2((k * 2^32 + t + 0.5) * 2^-52)
+  return lg2_approx(fmaf(__uint2float_rn(w >> 12), 9.5367431640625e-7f,
+                         fmaf(__uint2float_rn(t), 2.220446049250313e-16f, 1.1102230246251565e-16f)));
+}
+__device__ __forceinline__ float bm_theta(uint32_t w) {                   // (a / 4096) * 2 pi - pi
+  uint32_t fb;   // float in [1, 2): mantissa = a << 11
+  asm("lop3.b32 %0, %1, 0x007FF800, 0x3F800000, 0xEA;" : "=r"(fb) : "r"(w << 11));   // (x & mask) | exponent
+  return fmaf(__uint_as_float(fb), 6.283185307179586f, -9.42477796076938f);
+}
+// sigma * r of pair words w[0..NP) of one block, the far-tail refinement included (rare: one more Philox call)
+template <int NP>
+__device__ __forceinline__ void block_radii(const PhiloxKeys& rk, uint64_t frame, uint32_t block, uint32_t stream_word,
+                                            const uint32_t (&w)[NP], float c_scale, float (&r)[NP]) {
+  float l[NP];
+  uint32_t mn = w[0];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { l[i] = bm_lg2_u(w[i]); mn = min(mn, w[i]); }
+  if (mn < kTailWordLimit) {
+    const uint4 t = frame_words(rk, frame, block, tail_stream_word(stream_word));
+    const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+      if (w[i] < kTailWordLimit) l[i] = bm_lg2_u_tail(w[i], tw[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) r[i] = sqrt_approx(c_scale * l[i]);
 }
 
-// the first NP (1..3) pairs of one block -> z[0 .. 2*NP); written stage by stage (all lg2, all sqrt, all sin/cos) so
-// that the MUFU operations of the pairs are in flight together instead of queueing one by one
+// symbols 8*block .. 8*block + 2*NP - 1 of `frame`:  y[j] = fma(sigma r, cos/sin theta, bit j of `bits` ? +1 : -1)
 template <int NP>
-__device__ __forceinline__ void block_normals(const uint4 x, float* z) {
-  const uint32_t w[3] = {x.x, x.y, x.z};
-  float l[NP], th[NP], r[NP];
+__device__ __forceinline__ void block_symbols(const PhiloxKeys& rk, uint64_t frame, uint32_t block, uint32_t stream_word,
+                                              float c_scale, uint32_t bits, float* y) {
+  const uint4 x = frame_words(rk, frame, block, stream_word);
+  const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+  uint32_t w[NP];
+  float r[NP], th[NP];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) l[i] = bm_log2_u1(w[i]);
-  th[0] = bm_theta<0>(w[0], x.w);
-  if constexpr (NP > 1) th[1] = bm_theta<1>(w[1], x.w);
-  if constexpr (NP > 2) th[2] = bm_theta<2>(w[2], x.w);
-#pragma unroll
-  for (int i = 0; i < NP; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);   // sqrt(-2 ln u1)
+  for (int i = 0; i < NP; ++i) { w[i] = xw[i]; th[i] = bm_theta(xw[i]); }
+  block_radii<NP>(rk, frame, block, stream_word, w, c_scale, r);
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    z[2 * i] = r[i] * __cosf(th[i]);
-    z[2 * i + 1] = r[i] * __sinf(th[i]);
+    y[2 * i] = fmaf(r[i], __cosf(th[i]), ((bits >> (2 * i)) & 1u) ? 1.0f : -1.0f);
+    y[2 * i + 1] = fmaf(r[i], __sinf(th[i]), ((bits >> (2 * i + 1)) & 1u) ? 1.0f : -1.0f);
   }
 }
 
-// 6 standard normals of symbols 6*block .. 6*block+5 of `frame`
-__device__ __forceinline__ void noise6(const PhiloxKeys& rk, uint64_t frame, uint32_t block, uint32_t stream_word, float z[6]) {
-  block_normals<3>(frame_words(rk, frame, block, stream_word), z);
-}
-
-// the 14 normals of an L = 7 frame (blocks 0, 1 and the first pair of block 2): the three Philox chains first, then
-// the seven Box-Muller pairs stage by stage.  The three stages are separate functions so that a caller with idle time
-// in three places (the fused decoder's epilogue threads, between a hand-off to the tensor core and its completion)
-// can run one stage in each; noise14 is their composition, so both forms give the same bits.
+// The 14 symbols of an L = 7 frame (block 0 and the first three pairs of block 1) in three stages, so that a caller
+// with idle time in three places (the fused decoder's epilogue threads, between a hand-off to the tensor core and its
+// completion) can run one stage in each; frame14_symbols is their composition, so both forms give the same bits.
 struct Noise14Words {
-  uint32_t w[7];   // radius words of the seven pairs (low 5 bits: angle)
-  uint32_t a[3];   // word 3 of the three blocks (angle fields)
+  uint32_t w[7];
 };
 __device__ __forceinline__ void noise14_words(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, Noise14Words& n) {
   const uint4 x0 = frame_words(rk, frame, 0u, stream_word);
   const uint4 x1 = frame_words(rk, frame, 1u, stream_word);
-#ifdef NVD_EXP_TWO_CALLS   // timing experiment only (wrong noise): what a third Philox call costs
-  const uint4 x2 = make_uint4(x0.x ^ x1.y, x0.y ^ x1.z, x0.z ^ x1.w, x0.w ^ x1.x);
-#else
-  const uint4 x2 = frame_words(rk, frame, 2u, stream_word);
-#endif
-  n.w[0] = x0.x; n.w[1] = x0.y; n.w[2] = x0.z; n.w[3] = x1.x; n.w[4] = x1.y; n.w[5] = x1.z; n.w[6] = x2.x;
-  n.a[0] = x0.w; n.a[1] = x1.w; n.a[2] = x2.w;
+  n.w[0] = x0.x; n.w[1] = x0.y; n.w[2] = x0.z; n.w[3] = x0.w; n.w[4] = x1.x; n.w[5] = x1.y; n.w[6] = x1.z;
 }
-__device__ __forceinline__ void noise14_polar(const Noise14Words& n, float (&r)[7], float (&th)[7]) {
+__device__ __forceinline__ void noise14_polar(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, const Noise14Words& n,
+                                              float c_scale, float (&r)[7], float (&th)[7]) {
   float l[7];
+  uint32_t mn = n.w[0];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) l[i] = bm_log2_u1(n.w[i]);
-  th[0] = bm_theta<0>(n.w[0], n.a[0]); th[1] = bm_theta<1>(n.w[1], n.a[0]); th[2] = bm_theta<2>(n.w[2], n.a[0]);
-  th[3] = bm_theta<0>(n.w[3], n.a[1]); th[4] = bm_theta<1>(n.w[4], n.a[1]); th[5] = bm_theta<2>(n.w[5], n.a[1]);
-  th[6] = bm_theta<0>(n.w[6], n.a[2]);
+  for (int i = 0; i < 7; ++i) { l[i] = bm_lg2_u(n.w[i]); th[i] = bm_theta(n.w[i]); mn = min(mn, n.w[i]); }
+  if (mn < kTailWordLimit) {
+    const uint4 t0 = frame_words(rk, frame, 0u, tail_stream_word(stream_word));
+    const uint4 t1 = frame_words(rk, frame, 1u, tail_stream_word(stream_word));
+    const uint32_t tw[7] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z};
 #pragma unroll
-  for (int i = 0; i < 7; ++i) r[i] = sqrt_approx(-1.3862943611198906f * l[i]);
+    for (int i = 0; i < 7; ++i)
+      if (n.w[i] < kTailWordLimit) l[i] = bm_lg2_u_tail(n.w[i], tw[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = sqrt_approx(c_scale * l[i]);
 }
-__device__ __forceinline__ void noise14_finish(const float (&r)[7], const float (&th)[7], float z[14]) {
+__device__ __forceinline__ void noise14_symbols(const float (&r)[7], const float (&th)[7], uint32_t bits, float y[14]) {
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    z[2 * i] = r[i] * __cosf(th[i]);
-    z[2 * i + 1] = r[i] * __sinf(th[i]);
+    y[2 * i] = fmaf(r[i], __cosf(th[i]), ((bits >> (2 * i)) & 1u) ? 1.0f : -1.0f);
+    y[2 * i + 1] = fmaf(r[i], __sinf(th[i]), ((bits >> (2 * i + 1)) & 1u) ? 1.0f : -1.0f);
   }
 }
-__device__ __forceinline__ void noise14(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, float z[14]) {
+__device__ __forceinline__ void frame14_symbols(const PhiloxKeys& rk, uint64_t frame, uint32_t stream_word, float c_scale,
+                                                uint32_t bits, float y[14]) {
   Noise14Words n;
   float r[7], th[7];
   noise14_words(rk, frame, stream_word, n);
-  noise14_polar(n, r, th);
-  noise14_finish(r, th, z);
+  noise14_polar(rk, frame, stream_word, n, c_scale, r, th);
+  noise14_symbols(r, th, bits, y);
 }
 
 // ---- encoder on packed words ---------------------------------------------------------------

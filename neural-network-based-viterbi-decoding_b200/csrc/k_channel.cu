@@ -3,11 +3,11 @@
 // Replaces modulate_awgn (/root/reference/src/fnn_viterbi.py:224-253: x = float32(c), 0 -> -1,
 // y = x + np.random.normal(0, sigma)) and the per-frame Python loops that call it
 // (:380-388; fnn_viterbi_mixed_snr.py:452-460; fnn_viterbi_bitwise.py:309-317).  The noise of
-// symbol j of global frame f is Philox4x32-10(key = seed, counter = (f, j/6, snr_idx|stream)) — six symbols per
+// symbol j of global frame f is Philox4x32-10(key = seed, counter = (f, j/8, snr_idx|stream)) — eight symbols per
 // Philox call (frame_gen.cuh) — so a frame is reproducible from (seed, SNR index, frame index) on any GPU count.
 //
-// One thread = one (frame, 6-symbol block): 1 Philox call, 3 Box–Muller pairs, 6 outputs.
-// Consecutive threads write consecutive 6-symbol groups -> coalesced.  Algorithmic HBM traffic
+// One thread = one (frame, 8-symbol block): 1 Philox call, 4 Box–Muller pairs, 8 outputs, one coded byte in.
+// Consecutive threads write consecutive 8-symbol groups -> coalesced.  Algorithmic HBM traffic
 // per frame: ceil(n/8) B read + n*s B written (s = 2 bf16, 4 fp32/int32): 30 B / 58 B at n=14.
 #include "common.cuh"
 #include "frame_gen.cuh"
@@ -48,33 +48,27 @@ __global__ void __launch_bounds__(256) channel_kernel(const PhiloxKeys rk, const
   else f = t / nblk;
   const int blk = static_cast<int>(t - f * nblk);
   const int j0 = kNormalsPerBlock * blk;
-  const uint8_t* cb = coded + f * S + (j0 >> 3);
-  uint32_t two = __ldg(cb);
-  if ((j0 >> 3) + 1 < S) two |= static_cast<uint32_t>(__ldg(cb + 1)) << 8;
-  const uint32_t bits = (two >> (j0 & 7)) & 0x3Fu;
-  float z[6];
-  noise6(rk, frame0 + f, blk, stream_word, z);
-  float v[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) v[k] = fmaf(sigma, z[k], ((bits >> k) & 1u) ? 1.0f : -1.0f);
+  const uint32_t bits = __ldg(coded + f * S + blk);        // the block's eight code bits are byte `blk` of the packed row
+  float v[8];
+  block_symbols<4>(rk, frame0 + f, blk, stream_word, bm_scale(sigma), bits, v);
   T* row = y + f * row_stride + j0;
-  if (j0 + 6 <= n && (n & 1) == 0 && (row_stride & 1) == 0) {
-    // even n: rows start 4 B (bf16) / 8 B (fp32, int32) aligned -> three vector stores
+  if (j0 + 8 <= n && (n & 1) == 0 && (row_stride & 1) == 0) {
+    // even n: rows start 4 B (bf16) / 8 B (fp32, int32) aligned -> four vector stores
 #pragma unroll
-    for (int k = 0; k < 6; k += 2) {
+    for (int k = 0; k < 8; k += 2) {
       if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + k)[0] = __floats2bfloat162_rn(v[k], v[k + 1]);
       else if constexpr (kDtype == NVD_BF16_TRUNC) reinterpret_cast<__nv_bfloat162*>(row + k)[0] = __floats2bfloat162_rn(truncf(v[k]), truncf(v[k + 1]));
       else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + k)[0] = make_float2(v[k], v[k + 1]);
       else reinterpret_cast<int2*>(row + k)[0] = make_int2(cast_out<kDtype>(v[k]), cast_out<kDtype>(v[k + 1]));
     }
   } else {
-    for (int k = 0; k < 6 && j0 + k < n; ++k) row[k] = cast_out<kDtype>(v[k]);
+    for (int k = 0; k < 8 && j0 + k < n; ++k) row[k] = cast_out<kDtype>(v[k]);
   }
 }
 
 // Short frames (n <= 16 symbols, n even: the class decoders, L <= 8): one thread = one frame, the same
-// noise generation as the fused pipeline's producer warps — 3 Philox blocks and 7-8 Box-Muller pairs per thread
-// with no per-block index arithmetic (2.3x fewer instructions per frame than the block-per-thread kernel).
+// noise generation as the fused pipeline — 2 Philox blocks and 7-8 Box-Muller pairs per thread
+// with no per-block index arithmetic.
 // A warp's 32 rows are contiguous in y, so its 4- / 8-byte stores fill whole sectors between them.
 // kN: compile-time symbol count (14 for the reference L = 7: the unused Box-Muller pair and every bound check
 // disappear), 0 = run-time n
@@ -96,19 +90,17 @@ __global__ void __launch_bounds__(256) channel_frame_kernel(const PhiloxKeys rk,
   uint32_t bits = live ? __ldg(coded + f * S) : 0u;
   if (live && S > 1) bits |= static_cast<uint32_t>(__ldg(coded + f * S + 1)) << 8;
   T* row = &stage[wib][lane * n];
-  float z[18];
+  float v[16];
   if (kN == 14) {
-    noise14(rk, frame0 + f, stream_word, z);
+    frame14_symbols(rk, frame0 + f, stream_word, bm_scale(sigma), bits, v);
   } else {
-#pragma unroll
-    for (int blk = 0; blk < 3; ++blk)
-      if (kNormalsPerBlock * blk < n) noise6(rk, frame0 + f, blk, stream_word, z + kNormalsPerBlock * blk);
+    block_symbols<4>(rk, frame0 + f, 0u, stream_word, bm_scale(sigma), bits, v);
+    if (n > 8) block_symbols<4>(rk, frame0 + f, 1u, stream_word, bm_scale(sigma), bits >> 8, v + 8);
   }
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     if (j >= n) break;
-    const float a = fmaf(sigma, z[j], ((bits >> j) & 1u) ? 1.0f : -1.0f);
-    const float b = fmaf(sigma, z[j + 1], ((bits >> (j + 1)) & 1u) ? 1.0f : -1.0f);
+    const float a = v[j], b = v[j + 1];
     if constexpr (kDtype == NVD_BF16) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(a, b);
     else if constexpr (kDtype == NVD_BF16_TRUNC) reinterpret_cast<__nv_bfloat162*>(row + j)[0] = __floats2bfloat162_rn(truncf(a), truncf(b));
     else if constexpr (kDtype == NVD_F32) reinterpret_cast<float2*>(row + j)[0] = make_float2(a, b);

@@ -148,15 +148,16 @@ __device__ __forceinline__ void gen_stage(FrameGen& g, const KsParams& p, int b,
   const uint32_t c_hi = spread16(oa >> 16) | (spread16(ob >> 16) << 1);     // symbols 32..47
   const int valid_sym = 2 * remaining;                                      // symbols of this stage inside the frame
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    float z[6];
-    noise6(p.rk, g.frame, static_cast<uint32_t>(8 * b + nb), p.stream_word, z);
+  for (int nb = 0; nb < 6; ++nb) {       // six Philox blocks of eight symbols
+    constexpr int kPerBlock = kNormalsPerBlock;
+    const int j0 = kPerBlock * nb;                                          // symbol within the stage (compile time)
+    const uint32_t cw = j0 < 32 ? c_lo : c_hi;
+    float v[8];
+    block_symbols<4>(p.rk, g.frame, static_cast<uint32_t>(6 * b + nb), p.stream_word, bm_scale(p.sigma), cw >> (j0 & 31), v);
 #pragma unroll
-    for (int k = 0; k < 6; k += 2) {
-      const int j = 6 * nb + k;                                             // symbol within the stage (compile time)
-      const uint32_t cw = j < 32 ? c_lo : c_hi;
-      float a = fmaf(p.sigma, z[k], ((cw >> (j & 31)) & 1u) ? 1.0f : -1.0f);
-      float c = fmaf(p.sigma, z[k + 1], ((cw >> ((j + 1) & 31)) & 1u) ? 1.0f : -1.0f);
+    for (int k = 0; k < 8; k += 2) {
+      const int j = j0 + k;
+      float a = v[k], c = v[k + 1];
       if (p.trunc) { a = truncf(a); c = truncf(c); }
       w[j >> 1] = j < valid_sym ? pack2(a, c) : 0u;
     }

@@ -12,13 +12,17 @@ Counter / key convention shared with the CUDA side (csrc/frame_gen.cuh):
     key     = (seed & 0xffffffff, seed >> 32)
     counter = (frame & 0xffffffff, frame >> 32, block, (snr_idx << 8) | stream)
     stream  = STREAM_NOISE (1) for channel noise, STREAM_INFO (2) for source bits
-One call yields 4 words = 128 source bits, or the noise of SIX symbols 6*block .. 6*block+5: three
-Box-Muller pairs, pair i taking a 27-bit radius uniform from the top of word i and a 15-bit angle made of
-the low 5 bits of word i and bits [10i, 10i+10) of word 3 (42 bits per pair; the top two bits of word 3
-are unused).  27 bits put the largest radius at sqrt(2 * 28 * ln 2) = 6.23 sigma; 2^15 directions keep the
-angular lattice (1.9e-4 rad) far below the bf16 rounding of the stored symbol.  (Round 1 spent a whole
-32-bit word on each of radius and angle: 4 symbols per call; the Philox rounds are the dominant cost of
-every Monte-Carlo kernel, so the same 128 bits now feed 6.)
+One call yields 4 words = 128 source bits, or the noise of EIGHT symbols 8*block .. 8*block+7: four
+Box-Muller pairs, pair p made of word p alone — a 20-bit radius field k = w >> 12 and a 12-bit angle field
+a = w & 0xFFF:
+    u = (k + 0.5) * 2^-20,  theta = a * 2 pi / 4096 - pi,  r = sqrt(-2 ln u),  z = (r cos theta, r sin theta).
+Twenty bits alone would end the radius at 5.4 sigma on a coarse grid, so the sixteen lowest cells (k < 16,
+probability 1.5e-5 per pair) are refined by 32 more bits: word p of a second call on stream STREAM_NOISE_TAIL
+(same frame and block), u = (k * 2^32 + t + 0.5) * 2^-52 — radius up to 8.6 sigma, relative cell width <= 6 %
+everywhere.  The CUDA side makes that second call only when a thread meets such a word.  2^12 directions keep
+the angular lattice (1.5e-3 rad) below the bf16 rounding of the stored symbol.  (Round 1 spent a whole 32-bit
+word on each of radius and angle: 4 symbols per call; an earlier form of round 2 used 27 + 15 bits: 6 symbols
+per call.  The Philox rounds are the dominant cost of every Monte-Carlo kernel.)
 """
 from __future__ import annotations
 
@@ -30,6 +34,7 @@ W0 = np.uint32(0x9E3779B9)
 W1 = np.uint32(0xBB67AE85)
 STREAM_NOISE = 1
 STREAM_INFO = 2
+STREAM_NOISE_TAIL = 3
 DEFAULT_SEED = 20170710
 
 
@@ -66,29 +71,29 @@ def frame_words(seed: int, stream_word: int, frames: np.ndarray, block: int):
     )
 
 
-NORMALS_PER_BLOCK = 6
+NORMALS_PER_BLOCK = 8
+TAIL_CELLS = 16          # radius cells k < TAIL_CELLS take 32 refinement bits
 
 
-def box_muller(r_bits: np.ndarray, a_bits: np.ndarray):
-    """27-bit radius field, 15-bit angle field -> two N(0,1) draws; float64 statement of
-    csrc/frame_gen.cuh:
-        u1 = (r_bits + 0.5) * 2^-27            in (0,1)
-        th = int32(a_bits << 17) * pi * 2^-31  in [-pi, pi)
-        r  = sqrt(-2 ln u1);  z0 = r cos th;  z1 = r sin th
-    """
-    u1 = (r_bits.astype(np.float64) + 0.5) * 2.0 ** -27
-    th = (a_bits.astype(np.uint32) << np.uint32(17)).astype(np.int32).astype(np.float64) * (np.pi * 2.0 ** -31)
-    r = np.sqrt(-2.0 * np.log(u1))
+def box_muller(words: np.ndarray, tail_words: np.ndarray):
+    """Philox word (20-bit radius field | 12-bit angle field) and the refinement word of the same pair -> two
+    N(0,1) draws; float64 statement of csrc/frame_gen.cuh (bm_lg2_u, bm_lg2_u_tail, bm_theta)."""
+    w = np.asarray(words, dtype=np.uint32)
+    t = np.asarray(tail_words, dtype=np.uint32)
+    k = (w >> np.uint32(12)).astype(np.float64)
+    a = (w & np.uint32(0xFFF)).astype(np.float64)
+    u = np.where(k < TAIL_CELLS, (k * 2.0 ** 32 + t.astype(np.float64) + 0.5) * 2.0 ** -52, (k + 0.5) * 2.0 ** -20)
+    th = a * (2.0 * np.pi / 4096.0) - np.pi
+    r = np.sqrt(-2.0 * np.log(u))
     return r * np.cos(th), r * np.sin(th)
 
 
-def block_normals(x0, x1, x2, x3):
-    """Philox words of one call -> [.., 6] normals (symbols 6*block .. 6*block+5)."""
+def block_normals(x, t):
+    """Philox words of one call (x: 4 arrays) and of the refinement call (t: 4 arrays) -> [.., 8] normals
+    (symbols 8*block .. 8*block+7)."""
     out = []
-    for i, xi in enumerate((x0, x1, x2)):
-        r_bits = xi >> np.uint32(5)
-        a_bits = ((xi & np.uint32(31)) << np.uint32(10)) | ((x3 >> np.uint32(10 * i)) & np.uint32(1023))
-        out.extend(box_muller(r_bits, a_bits))
+    for xi, ti in zip(x, t):
+        out.extend(box_muller(xi, ti))
     return np.stack(out, axis=-1)
 
 
@@ -98,8 +103,9 @@ def noise_normals(seed: int, snr_idx: int, frames: np.ndarray, n: int) -> np.nda
     nblk = (n + NORMALS_PER_BLOCK - 1) // NORMALS_PER_BLOCK
     out = np.empty((frames.shape[0], NORMALS_PER_BLOCK * nblk), dtype=np.float64)
     sw = ((snr_idx & 0xFFFFFF) << 8) | STREAM_NOISE
+    sw_tail = ((snr_idx & 0xFFFFFF) << 8) | STREAM_NOISE_TAIL
     for blk in range(nblk):
-        out[:, 6 * blk:6 * blk + 6] = block_normals(*frame_words(seed, sw, frames, blk))
+        out[:, 8 * blk:8 * blk + 8] = block_normals(frame_words(seed, sw, frames, blk), frame_words(seed, sw_tail, frames, blk))
     return out[:, :n]
 
 
