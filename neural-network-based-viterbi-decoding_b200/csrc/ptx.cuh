@@ -122,6 +122,10 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// producer side of a producer/consumer barrier: counts as an arrival, does not wait
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // ---- tcgen05 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
