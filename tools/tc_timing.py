@@ -6,9 +6,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "neural-network-based-viterbi-decoding_b200"))
 from nvd import montecarlo, weights, _lib
 
-names = ["top", "wait-full", "issue1", "wait1", "epi1", "sync", "issue2", "wait2",
-         "epi2+sync", "issue3+wait3", "epi3+sync", "issue4+wait4", "argmax"]
-STAMPS = [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14]
+names = ["top", "-", "-", "wait1", "epi1", "handoff2", "gen1 (Philox)", "wait2",
+         "epi2+handoff3", "gen2 (radii)", "wait3", "epi3+handoff4", "gen3 (symbols)", "wait4", "argmax"]
+STAMPS = [0, 1, 2, 3, 4, 5, 8, 9, 10, 6, 11, 12, 7, 13, 14]
 with montecarlo.Simulator(0) as sim:
     h = sim.load_mlp(weights.load_default_fnn())
     st = np.zeros(64 * 4 * 16, dtype=np.uint64)
