@@ -294,8 +294,20 @@ int nvd_comm_init(nvd_ctx* ctx, int rank, int world, const void* id);
 int nvd_comm_destroy(nvd_ctx* ctx);
 int nvd_comm_info(nvd_ctx* ctx, int* rank, int* world, int* nccl_version);
 /* in-place sum over all ranks of n uint64 values in DEVICE memory (e.g. the [n_snr][4] counters of nvd_mc_run);
- * asynchronous on the context's stream; a no-op on a context without a communicator. */
+ * asynchronous on the context's stream; a no-op on a context without a communicator.  Goes over NVLink peer memory
+ * when nvd_comm_p2p_open has succeeded (n <= 448), else through ncclAllReduce. */
 int nvd_comm_allreduce_u64(nvd_ctx* ctx, uint64_t* values_dev, size_t n);
+/* The same exchange without NCCL, over NVLink / NVSwitch peer memory: every rank owns an 8 KB exchange block; a
+ * small kernel adds the rank's values into every rank's block with system-scope atomics and raises every rank's
+ * arrival counter, a second one waits for all arrivals (csrc/comm.cu).  ~10 us for 8 ranks.
+ *   all ranks: nvd_comm_p2p_handle(ctx, h)  ->  gather the NVD_COMM_IPC_BYTES bytes of every rank, in rank order
+ *              (any host channel)  ->  nvd_comm_p2p_open(ctx, rank, world, handles)
+ * NVD_ERR_UNSUPPORTED when a peer's block cannot be mapped (GPU not visible to this process, no P2P path): keep
+ * using the NCCL transport then.  world = 1 is allowed (the kernels run against the rank's own block). */
+#define NVD_COMM_IPC_BYTES 64
+int nvd_comm_p2p_handle(nvd_ctx* ctx, void* handle_out);
+int nvd_comm_p2p_open(nvd_ctx* ctx, int rank, int world, const void* handles);
+int nvd_comm_p2p_close(nvd_ctx* ctx);   /* unmap the peers and free the block (all ranks, after a host barrier) */
 
 /* Deep-BER driver (BASELINE.json configs[4]): per SNR point, chunks of `chunk_frames` GLOBAL frames are added until
  * the point has >= min_frame_errors frame errors (globally, after the all-reduce) or max_frames frames.  With a

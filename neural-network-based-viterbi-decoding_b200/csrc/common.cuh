@@ -16,6 +16,11 @@
 
 namespace nvd {
 
+constexpr int kMaxPeers = 16;                   // ranks of one NVLink domain
+constexpr int kXchgValues = 448;                // uint64 values per exchange (two alternating data areas per block)
+constexpr int kXchgBytes = 8192;                // [0, 3584) area 0 | [3584, 7168) area 1 | 7168: arrival counter
+
+
 void set_error(const char* fmt, ...);
 
 #define NVD_CUDA(expr)                                                                       \
@@ -130,6 +135,12 @@ struct nvd_ctx {
   // multi-GPU exchange step: NCCL communicator of this context's rank (comm.cu); null = single GPU
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  // ... and the same exchange over NVLink peer memory (comm.cu, nvd_comm_p2p_*): every rank owns one exchange block
+  // (cudaMalloc, exported with CUDA IPC) and maps the blocks of all the others
+  uint64_t* xchg_local = nullptr;                 // this rank's block (kXchgBytes)
+  uint64_t* xchg_peer[nvd::kMaxPeers] = {};            // every rank's block as seen from here ([comm_rank] = xchg_local)
+  int xchg_world = 0;                             // 0 = peer exchange not set up
+  uint64_t xchg_epoch = 0;                        // exchanges queued so far (all ranks call them in the same order)
   // staged-pipeline stage timing
   cudaEvent_t stage_ev[6] = {nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};

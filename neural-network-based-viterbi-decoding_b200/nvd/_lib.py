@@ -20,6 +20,7 @@ PREC_FP32, PREC_BF16_TC = 0, 1
 MC_STAGED, MC_FUSED = 0, 1
 COUNT_PRED_IS_MSB_CLASS = 1
 COMM_ID_BYTES = 128
+COMM_IPC_BYTES = 64
 
 CODES = {"57": CODE_57_REF, "57_ref": CODE_57_REF, "133171": CODE_133171, "57_causal": CODE_57_CAUSAL}
 DTYPES = {"f32": F32, "bf16": BF16, "i32_trunc": I32_TRUNC, "bf16_trunc": BF16_TRUNC}
@@ -111,6 +112,9 @@ _PROTOS = {
     "nvd_comm_destroy": ([_vp], _i),
     "nvd_comm_info": ([_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)], _i),
     "nvd_comm_allreduce_u64": ([_vp, _vp, C.c_size_t], _i),
+    "nvd_comm_p2p_handle": ([_vp, _vp], _i),
+    "nvd_comm_p2p_open": ([_vp, _i, _i, _vp], _i),
+    "nvd_comm_p2p_close": ([_vp], _i),
     "nvd_mc_sweep": ([_vp, C.POINTER(McConfig), C.POINTER(_f), C.POINTER(C.c_int32), _i, _u64, _u64, _u64, _vp], _i),
     "nvd_debug_tc_timing": ([_vp, _i, _u64, _vp], _i),
     "nvd_debug_umma_probe_ts": ([_vp, _i, _i, _i, _vp, _vp, _vp], _i),

@@ -78,6 +78,23 @@ def broadcast_bytes(data: bytes | None, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
+def all_gather_bytes(data: bytes, nbytes: int) -> bytes:
+    """Every rank contributes `nbytes` bytes; returns the concatenation in rank order (the CUDA IPC handles of
+    nvd_comm_p2p_open)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return bytes(data)
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).clone()
+    out = [torch.zeros(nbytes, dtype=torch.uint8) for _ in range(dist.get_world_size())]
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        out = [o.cuda() for o in out]
+    dist.all_gather(out, t)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+
 def barrier():
     import torch.distributed as dist
 

@@ -8,6 +8,8 @@ exchange is one all-reduce(sum) of the [n_snr, 4] uint64 counters.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 
@@ -91,6 +93,7 @@ class Simulator:
         self._bufs = []
         self._n_out = {}
         self.rank, self.world = 0, 1
+        self.p2p = False
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
@@ -146,11 +149,31 @@ class Simulator:
         raw = broadcast(raw, _lib.COMM_ID_BYTES)
         check(self.lib.nvd_comm_init(self.ctx, rank, world, C.create_string_buffer(raw, _lib.COMM_ID_BYTES)))
         self.rank, self.world = rank, world
+        if os.environ.get("NVD_P2P", "1") != "0":
+            self.comm_p2p_open(rank, world)
+
+    def comm_p2p_open(self, rank: int, world: int, all_gather=None) -> bool:
+        """Map every rank's exchange block (CUDA IPC) so that nvd_comm_allreduce_u64 goes over NVLink peer memory
+        instead of NCCL.  `all_gather(bytes, nbytes) -> bytes` concatenates the ranks' handles in rank order (default:
+        torch.distributed).  Returns False — and the NCCL transport stays in use — when a peer cannot be mapped; the
+        decision is made collectively, so that all ranks use the same transport."""
+        if all_gather is None:
+            from . import dist
+            all_gather = dist.all_gather_bytes
+        buf = C.create_string_buffer(_lib.COMM_IPC_BYTES)
+        check(self.lib.nvd_comm_p2p_handle(self.ctx, buf))
+        handles = all_gather(buf.raw, _lib.COMM_IPC_BYTES)
+        status = self.lib.nvd_comm_p2p_open(self.ctx, rank, world, C.create_string_buffer(handles, len(handles)))
+        oks = all_gather(bytes([1 if status == 0 else 0]), 1)
+        self.p2p = all(b == 1 for b in oks)
+        if status == 0 and not self.p2p:            # somebody else failed: everybody goes back to NCCL
+            check(self.lib.nvd_comm_p2p_close(self.ctx))
+        return self.p2p
 
     def comm_info(self):
         r, w, v = C.c_int(), C.c_int(), C.c_int()
         check(self.lib.nvd_comm_info(self.ctx, C.byref(r), C.byref(w), C.byref(v)))
-        return dict(rank=r.value, world=w.value, nccl_version=v.value)
+        return dict(rank=r.value, world=w.value, nccl_version=v.value, transport="nvlink-peer-memory" if self.p2p else "nccl")
 
     def allreduce_counters(self, counters: "DeviceBuffer", n_u64: int):
         """In-place ncclAllReduce(sum) of n uint64 device values on the library's stream (asynchronous)."""

@@ -187,3 +187,25 @@ def test_ber_sweep_57_matches_oracle(sim):
     b = sim.run(h, "57", 7, [0.0, 3.0, 6.0], n, 0, mode="staged", precision="bf16")
     assert (a == b).all() and a[0, 0] > a[1, 0] > a[2, 0]
     assert bf16[0, 0] / bf16[0, 3] < 0.2
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_single_rank():
+    """csrc/comm.cu peer-memory all-reduce with world = 1 (the kernels run against the rank's own exchange block):
+    identity on the values, no carry-over between exchanges (the two alternating areas are cleared), any n up to 448,
+    and the Monte-Carlo counters pass through it unchanged."""
+    from nvd import montecarlo
+    with montecarlo.Simulator(0) as s:
+        assert s.comm_p2p_open(0, 1, all_gather=lambda b, n: bytes(b))
+        assert s.comm_info()["transport"] == "nvlink-peer-memory"
+        rng = np.random.default_rng(11)
+        for rnd in range(9):
+            n = [4, 448, 1, 36, 100][rnd % 5]
+            mine = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+            buf = s.to_device(mine)
+            s.allreduce_counters(buf, n)
+            assert np.array_equal(buf.download(np.uint64, (n,)), mine), (rnd, n)
+            s.free(buf)
+        big = s.to_device(np.arange(449, dtype=np.uint64))        # above the block's capacity: the NCCL path, a no-op without a communicator
+        s.allreduce_counters(big, 449)
+        assert np.array_equal(big.download(np.uint64, (449,)), np.arange(449, dtype=np.uint64))
