@@ -76,24 +76,31 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.ok = False
 
+    def sample(self, force=False):
+        """One NVML reading; kept when the sampler is active (or forced: the main thread samples the short headline
+        region itself, while its launches run, so that the region never ends up without a reading)."""
+        if not self.ok:
+            return
+        try:
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            if self.active or force:
+                self.samples.append(float(mhz))
+                try:
+                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+        except Exception:
+            pass
+
     def run(self):
         if not self.ok:
             return
         while not self.stop_flag:
-            try:
-                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
-                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                if self.active:
-                    self.samples.append(float(mhz))
-                    try:
-                        self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-                    except Exception:
-                        pass
-                    for bit, name in self.REASONS.items():
-                        if mask & bit:
-                            self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample()
             time.sleep(float(os.environ.get("NVD_BENCH_CLOCK_PERIOD_S", "0.005")))
 
     def reset(self):
@@ -240,6 +247,11 @@ def main():
     # counters, queued behind the last launch (no host bounce) — inside the timed region
     sim.allreduce_counters(counters, 4)
     sim.record(e2)
+    # everything above is queued, nothing has been waited for: read the clocks while the K steps run
+    t_region = (args.preroll + args.steps) * 0.9e-3
+    for i in range(4):
+        time.sleep(t_region * (0.3 if i == 0 else 0.15))
+        sampler.sample(force=True)
     sim.sync()
     fused_ms = sim.elapsed_ms(e0, e2)
     ar_ms = sim.elapsed_ms(e1, e2) if world > 1 else 0.0
@@ -249,6 +261,8 @@ def main():
     dist.barrier()
     step_ms = dist.all_reduce_max(fused_ms / args.steps)
     kernel_ms = dist.all_reduce_max(kernels_ms / args.steps)
+    kernel_ms_min = -dist.all_reduce_max(-kernels_ms / args.steps)        # fastest rank: the spread is GPU-to-GPU variation
+    ar_ms_min = -dist.all_reduce_max(-ar_ms)                              # the exchange as seen by the LAST rank to arrive
     value = world * frames * L / (step_ms * 1e-3) / 1e9
 
     # ---------------- end to end: host buffers through nvd_mc_run_host -------------------------------
@@ -527,6 +541,10 @@ def main():
         "clocks": clocks,
         "ber": ber, "frame_errors": int(total_counts[0, 1]), "frames_total": int(total_counts[0, 2]),
         "allreduce_ms": ar_ms,
+        "ranks": {"kernel_ms_per_step_max": kernel_ms, "kernel_ms_per_step_min": kernel_ms_min,
+                  "exchange_ms_rank0": ar_ms, "exchange_ms_min_over_ranks": ar_ms_min,
+                  "note": "kernel = e0..e1 (K launches) per rank; exchange = e1..e2: the waiting for slower ranks is inside it on "
+                          "every rank but the slowest, whose figure is the cost of the exchange itself"},
         "comm": sim.comm_info(),
         "staged": staged,
         "sustained": sustained,
