@@ -323,8 +323,9 @@ int nvd_mc_sweep(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_hos
  * and descriptor strides; used by tests/test_gpu_kernels.py::test_umma_layout_probe to pin the UMMA shared-memory
  * layout the tensor-core kernel relies on.  a_image_host: 4096 B, b_image_host: N*32 B,
  * d_host: [128, N] fp32. */
-/* phase time stamps (clock64) of CTA 0's four groups over their first 64 tiles of a fused run:
- * stamps_host[(tile * 4 + group) * 16 + phase]. */
+/* phase time stamps (clock64) of CTA 0's groups over their first 64 tiles of a fused run:
+ * stamps_host[(tile * groups_per_cta + group) * 16 + phase], and behind them, from index 4096, every group's
+ * [start ns, finish ns, tiles, SM id] (global timer), group index = CTA * groups_per_cta + group.  8192 values. */
 int nvd_debug_tc_timing(nvd_ctx* ctx, int model, uint64_t frames, uint64_t* stamps_host);
 /* same with the A operand in TENSOR MEMORY (written by tcgen05.st, K elements packed two bf16 per
  * column): a_rows_host = [128][8] uint32. */
