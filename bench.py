@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_kernel<MODE_FUSED> launch
 # (profiles/r1_ncu_full_fused_summary.txt): the 40 KB weight image and the parameters, nothing per frame
-NCU_DRAM_BYTES_PER_LAUNCH = 88064     # 88 320 and 87 808 B in the two captured launches
+NCU_DRAM_BYTES_PER_LAUNCH = 85632     # 85 760 and 85 504 B in the two captured launches (profiles/r2_ncu_full_fused_summary.txt)
 
 
 def main():
@@ -509,9 +509,10 @@ def main():
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "mlp_tc_kernel<MODE_FUSED>",
                 "peak_source": peaks["source"] + (", sustained" if long_region else ", burst"),
                 "note": "traffic = dram bytes per launch from the committed ncu --set full capture (weights only: the fused "
-                        "kernel generates its frames on chip); not HBM-bound.  Co-limited by MUFU (140 tanh + 28 RNG "
-                        "transcendentals per frame after the FMA-pipe polynomial takes 3/8 of the tanh), the fixed cost of "
-                        "18 small tcgen05.mma per tile and four dependent MMA->epilogue hand-offs per tile (DESIGN.md §4)"}
+                        "kernel generates its frames on chip); not HBM-bound.  Bound by the instruction stream of its 16 "
+                        "epilogue warps per SM (~1 160 instructions per frame, 168 of them MUFU: 140 tanh after the FMA-pipe "
+                        "polynomial takes 3/8 of them + 28 for the channel noise); MUFU pipe 65 %, issue slots 56 %, tensor "
+                        "pipe 30 % busy (DESIGN.md §4)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
