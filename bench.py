@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU")
-    ap.add_argument("--preroll", type=int, default=4,
+    ap.add_argument("--preroll", type=int, default=6,
                     help="untimed launches queued between the barrier + synchronize and the first timed step (the GPU's clocks "
                          "sag while it idles in the barrier)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,15 +230,16 @@ def main():
     sim.sync()
     sampler.active = True
     _lb.check(sim.lib.nvd_memset(sim.ctx, counters.ptr, 0, 32))       # asynchronous, on the library's stream
-    # ranks leave the host barrier tens of microseconds apart; one more (tiny) all-reduce on the library's stream
-    # makes every rank's stream pass the same point together, so the regions start aligned on the DEVICE
-    sim.allreduce_counters(align, 4)
     # The barrier + synchronize above idle the GPU, and after an idle gap the first four launches run 1-12 % slow while
     # the clocks come back (tools/diag/gap_probe.py: 1.065 / 0.988 / 0.973 / 0.962 ms against 0.955).  A Monte-Carlo
     # job never idles between its launches, so the timed K steps start behind `preroll` more untimed warm-up launches
-    # queued on the same stream (their counters are discarded); e0 is recorded behind them.
+    # queued on the same stream (their counters are discarded).
     for w in range(args.preroll):
         sim.run_async(h, "133171", L, [SNR_DB], frames, align, frame0 + w * world * frames, mode="fused")
+    # Ranks leave the host barrier tens of microseconds apart and run the pre-roll at slightly different speeds; one
+    # (tiny) exchange on the library's stream right in front of the first event makes every rank's stream pass the
+    # same point together, so the regions start aligned on the DEVICE (the gap it leaves is ~20 us: no clock sag).
+    sim.allreduce_counters(align, 4)
     sim.record(e0)
     for s in range(args.steps):
         sim.run_async(h, "133171", L, [SNR_DB], frames, counters, frame0 + s * world * frames, mode="fused")

@@ -8,5 +8,6 @@ N="${1:-8}"
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 NCCL_DEBUG=WARN timeout 300 $RUN bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench exit $?"
 tail -c 1500 gpurun_out/bench_n$N.json | head -c 600; echo
+[ "${SKIP_TRACE:-0}" = "1" ] && exit 0
 NVD_HOST_STEP_TRACE=1 timeout 200 $RUN bench.py --gpus $N --steps 5 --warmup 3 --no-legs --no-staged --no-cpu-baseline > gpurun_out/trace_n$N.json 2> gpurun_out/trace_n$N.err; echo "trace exit $?"
 grep -c "host step trace" gpurun_out/trace_n$N.err
