@@ -244,7 +244,7 @@ def main():
     for s in range(args.steps):
         sim.run_async(h, "133171", L, [SNR_DB], frames, counters, frame0 + s * world * frames, mode="fused")
     sim.record(e1)
-    # the path's one exchange step: ncclAllReduce(sum, uint64[4]) on the library's stream, directly on the device
+    # the path's one exchange step: sum of uint64[4] over all ranks (NVLink peer memory, or ncclAllReduce) on the library's stream, directly on the device
     # counters, queued behind the last launch (no host bounce) — inside the timed region
     sim.allreduce_counters(counters, 4)
     sim.record(e2)

@@ -101,7 +101,7 @@ int nvd_encode(nvd_ctx* ctx, int code, const uint8_t* info_packed, int L, int64_
 
 /* ---- K2 channel: replaces modulate_awgn (src/fnn_viterbi.py:224-253) + the per-frame Python
  * loops that call it (:380-388).  y[b, j] = (2c-1) + sigma * N(0,1), noise = Philox4x32-10 keyed
- * by (seed; frame0+b, j/6, snr_idx) — six symbols per Philox call.  y is [B, n] dense in out_dtype
+ * by (seed; frame0+b, j/8, snr_idx) — eight symbols per Philox call (csrc/frame_gen.cuh).  y is [B, n] dense in out_dtype
  * (NVD_F32/BF16/I32_TRUNC). */
 int nvd_channel(nvd_ctx* ctx, const uint8_t* coded_packed, int n, int64_t B, float sigma,
                 int snr_idx, uint64_t frame0, int out_dtype, void* y);
@@ -283,7 +283,7 @@ int nvd_train_end(nvd_ctx* ctx, int trainer, float* const* W_host, float* const*
  * The reference is single-process; the path shards by global frame range, one context (process or
  * thread) per GPU, and the ONLY exchange is the sum of the error counters that calculate_error / calculate_ber
  * (src/fnn_viterbi.py:619-674, src/fnn_viterbi_mixed_snr.py:634-655) would have computed over the whole test set.
- * It is an ncclAllReduce(ncclUint64, ncclSum) over NVLink queued on the context's stream right behind the launches
+ * It is a sum of uint64 values over NVLink (peer memory, or ncclAllReduce) queued on the context's stream right behind the launches
  * that produce the counters.  NCCL is bound at run time (dlopen of libnccl.so.2; NVD_NCCL_LIB overrides): a host
  * without NCCL can still use every single-GPU entry point.
  *   rank 0:    nvd_comm_unique_id(id)  ->  ship the NVD_COMM_ID_BYTES bytes to the other ranks (any host channel)

@@ -176,7 +176,8 @@ class Simulator:
         return dict(rank=r.value, world=w.value, nccl_version=v.value, transport="nvlink-peer-memory" if self.p2p else "nccl")
 
     def allreduce_counters(self, counters: "DeviceBuffer", n_u64: int):
-        """In-place ncclAllReduce(sum) of n uint64 device values on the library's stream (asynchronous)."""
+        """In-place sum over all ranks of n uint64 device values on the library's stream (asynchronous): over NVLink
+        peer memory when comm_p2p_open succeeded, else ncclAllReduce."""
         check(self.lib.nvd_comm_allreduce_u64(self.ctx, counters.ptr, n_u64))
 
     # -- memory / timing -------------------------------------------------------------------------
