@@ -24,10 +24,15 @@ WORKER = textwrap.dedent("""
     c = opipe.mc_step(Ws, bs, [1, 1, 1, 1], 7, oenc.CODE_133171, 2.0, lo, n, noise="philox")
     tot = dist.all_reduce_sum(c.astype(np.int64))
     worst = dist.all_reduce_max(float(rank))
+    # the byte channels of the exchange set-up: NCCL id from rank 0, CUDA IPC handles from everybody in rank order
+    ident = dist.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128)
+    handles = dist.all_gather_bytes(bytes([rank * 16 + i for i in range(64)]), 64)
     dist.barrier()
     if rank == 0:
         whole = opipe.mc_step(Ws, bs, [1, 1, 1, 1], 7, oenc.CODE_133171, 2.0, frame0, N, noise="philox")
-        print(json.dumps(dict(tot=tot.tolist(), whole=whole.astype(np.int64).tolist(), worst=worst)))
+        print(json.dumps(dict(tot=tot.tolist(), whole=whole.astype(np.int64).tolist(), worst=worst,
+                              ident_ok=ident == bytes(range(128)),
+                              handles_ok=handles == bytes([r * 16 + i for r in range(world) for i in range(64)]))))
     dist.shutdown()
 """)
 
@@ -47,4 +52,5 @@ def test_two_rank_sharding_and_allreduce(tmp_path):
     res = json.loads(outs[0][0].strip().splitlines()[-1])
     assert res["tot"] == res["whole"]          # counters independent of the split
     assert res["worst"] == 1.0
+    assert res["ident_ok"] and res["handles_ok"]
     assert res["tot"][2] == 6001 and res["tot"][3] == 6001 * 7
