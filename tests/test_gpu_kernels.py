@@ -142,6 +142,37 @@ def test_channel_matches_oracle(sim, n, B, frame0, snr_idx):
     assert ((goti == np.trunc(want).astype(np.int32)) | near_int).all()
 
 
+def test_channel_far_tail_refinement_matches_oracle(sim):
+    """Radius cells k < 16 (probability 1.5e-5 per pair) take 32 more bits from a second Philox call that only the
+    threads meeting such a word make: find frames with such words by the oracle's generator and hold the frame kernel
+    (n = 14), the block kernel (n = 40) and its ragged tail to the oracle exactly there."""
+    from oracle import philox
+    snr_idx, B = 2, 1 << 19
+    frames = np.arange(B, dtype=np.uint64)
+    sw = (snr_idx << 8) | philox.STREAM_NOISE
+    hits = np.zeros(B, bool)
+    for blk in range(5):                                        # n = 40 symbols = 5 blocks of 8
+        for w in philox.frame_words(SEED, sw, frames, blk):
+            hits |= (w >> np.uint32(12)) < philox.TAIL_CELLS
+    rows = np.flatnonzero(hits)
+    assert len(rows) >= 20                                      # ~ 2^19 * 20 pairs * 1.5e-5 = 160 expected
+    sigma = 0.8
+    for n in (14, 40, 37):
+        worst = 0.0
+        for f in rows[:24]:
+            f0 = int(f) - 3                                     # the hit sits inside a small batch, not at its edge
+            if f0 < 0:
+                continue
+            coded = ((np.arange(8 * n).reshape(8, n) * 7 + int(f)) % 3 == 0).astype(np.uint8)
+            want = ochan.channel_philox(coded, sigma, SEED, snr_idx, f0, ochan.OUT_F32)
+            got = sim.channel_bits(coded, sigma, snr_idx, f0, "f32")
+            worst = max(worst, float(np.abs(got - want).max()))
+        assert worst < 1e-3, (n, worst)
+    # and the tail is really there: the largest radius among the hit frames exceeds what a bare 20-bit field could give
+    z = philox.noise_normals(SEED, snr_idx, rows[:200].astype(np.uint64), 40)
+    assert np.sqrt(z[:, 0::2] ** 2 + z[:, 1::2] ** 2).max() > 4.7
+
+
 def test_channel_moments_and_bpsk(sim):
     B, n = 1 << 16, 14
     zeros = np.zeros((B, n), np.uint8)
