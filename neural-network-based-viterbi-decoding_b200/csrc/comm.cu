@@ -153,6 +153,10 @@ void xchg_release(nvd_ctx* ctx) {
 int comm_allreduce_u64(nvd_ctx* ctx, uint64_t* values_dev, size_t n) {
   if (n == 0) return NVD_OK;
   if (ctx->xchg_world >= 1 && n <= static_cast<size_t>(kXchgValues)) return xchg_allreduce_u64(ctx, values_dev, n);
+  if (ctx->xchg_world > 1 && !ctx->comm) {       // more values than an exchange block holds, and no second transport
+    set_error("nvd_comm_allreduce_u64: %zu values exceed the peer exchange block (%d) and there is no NCCL communicator", n, kXchgValues);
+    return NVD_ERR_UNSUPPORTED;
+  }
   if (!ctx->comm || ctx->comm_world <= 1) return NVD_OK;
   NVD_NCCL(g_nccl.AllReduce(values_dev, values_dev, n, kNcclUint64, kNcclSum, static_cast<NcclComm>(ctx->comm), ctx->stream));
   return NVD_OK;
