@@ -971,7 +971,10 @@ int nvd_mc_sweep(nvd_ctx* ctx, const nvd_mc_config* cfg, const float* snr_db_hos
       c.frame0 = cfg->frame0 + done + lo;
       c.frames = hi - lo;
       NVD_CUDA(cudaMemsetAsync(d_chunk, 0, 4 * sizeof(uint64_t), ctx->stream));
-      NVD_TRY(nvd_mc_run(ctx, &c, snr_db_host + i, &idx, 1, d_chunk));
+      ctx->isolated_launches = true;             // the host decides after every chunk: no launch follows this one directly
+      const int run_status = nvd_mc_run(ctx, &c, snr_db_host + i, &idx, 1, d_chunk);
+      ctx->isolated_launches = false;
+      NVD_TRY(run_status);
       NVD_TRY(comm_allreduce_u64(ctx, d_chunk, 4));
       NVD_CUDA(queue_tail_copy(ctx));
       NVD_TRY(finish_tail(ctx));

@@ -113,6 +113,7 @@ struct nvd_ctx {
   std::vector<nvd::LstmModel> lstms;
   std::vector<nvd_trainer> trainers;
   // device-side abort flag written by kernels whose bounded waits expire
+  bool isolated_launches = false;  // set by callers that synchronise after every fused launch (k_mlp_tc.cu: launch_mlp_tc_fused)
   int* abort_flag = nullptr;       // device
   int* abort_flag_host = nullptr;  // pinned mirror
   // scratch owned by the context (grown on demand)
