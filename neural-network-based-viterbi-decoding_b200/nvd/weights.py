@@ -9,7 +9,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import _lib
+from . import _lib, tf_bundle
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 WEIGHTS_DIR = os.path.join(os.path.dirname(_HERE), "weights")
@@ -102,12 +102,32 @@ def save_mlp(path: str, model: MlpModel) -> None:
 
 
 def load_mlp(path: str) -> MlpModel:
-    z = np.load(path)
-    keys = [k for k in _LAYER_KEYS if f"weights_{k}" in z.files]
-    Ws = [z[f"weights_{k}"].astype(np.float32) for k in keys] + [z["weights_out"].astype(np.float32)]
-    bs = [z[f"bias_{k}"].astype(np.float32) for k in keys] + [z["bias_out"].astype(np.float32)]
-    acts = z["acts"].tolist() if "acts" in z.files else [_lib.ACT_TANH] * len(Ws)
-    return MlpModel(Ws, bs, acts, meta={"path": path})
+    """`.npz` written by save_mlp, or — when there is no such file but `<path minus .npz>.index` exists — a TensorFlow
+    checkpoint as the reference's tf.train.Saver writes it (nvd/tf_bundle.py; variables weights_h1.., bias_h1..,
+    weights_out, bias_out as named in src/fnn_viterbi_mixed_snr.py:533-567; optimizer slots are ignored)."""
+    prefix = path[:-4] if path.endswith(".npz") else path
+    if not os.path.exists(path) and tf_bundle.is_bundle(prefix):
+        z = tf_bundle.read_bundle(prefix)
+        files = set(z)
+        meta = {"path": prefix, "format": "tf-bundle"}
+    else:
+        z = np.load(path)
+        files = set(z.files)
+        meta = {"path": path}
+    keys = [k for k in _LAYER_KEYS if f"weights_{k}" in files]
+    Ws = [np.asarray(z[f"weights_{k}"], dtype=np.float32) for k in keys] + [np.asarray(z["weights_out"], dtype=np.float32)]
+    bs = [np.asarray(z[f"bias_{k}"], dtype=np.float32) for k in keys] + [np.asarray(z["bias_out"], dtype=np.float32)]
+    acts = np.asarray(z["acts"]).tolist() if "acts" in files else [_lib.ACT_TANH] * len(Ws)
+    return MlpModel(Ws, bs, acts, meta=meta)
+
+
+def save_tf_checkpoint(prefix: str, model: MlpModel) -> None:
+    """The model's variables as a TensorFlow checkpoint (`<prefix>.index` + `.data-00000-of-00001`) under the names the
+    reference's graphs give them, so that `saver.restore(sess, prefix)` there finds them."""
+    w, b = to_dicts(model)
+    tensors = {f"weights_{k}": v for k, v in w.items()}
+    tensors.update({("bias_" + (k if k == "out" else "h" + k[1:])): v for k, v in b.items()})
+    tf_bundle.write_bundle(prefix, {k: np.asarray(v, dtype=np.float32) for k, v in tensors.items()})
 
 
 def load_default_fnn() -> MlpModel:
