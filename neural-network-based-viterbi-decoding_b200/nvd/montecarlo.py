@@ -163,6 +163,10 @@ class Simulator:
         buf = C.create_string_buffer(_lib.COMM_IPC_BYTES)
         check(self.lib.nvd_comm_p2p_handle(self.ctx, buf))
         handles = all_gather(buf.raw, _lib.COMM_IPC_BYTES)
+        if len(handles) != world * _lib.COMM_IPC_BYTES:      # no channel that reaches every rank (e.g. torch.distributed not
+            self.p2p = False                                 # initialised and no all_gather given): stay on NCCL
+            check(self.lib.nvd_comm_p2p_close(self.ctx))
+            return False
         status = self.lib.nvd_comm_p2p_open(self.ctx, rank, world, C.create_string_buffer(handles, len(handles)))
         oks = all_gather(bytes([1 if status == 0 else 0]), 1)
         self.p2p = all(b == 1 for b in oks)
