@@ -539,7 +539,8 @@ def main():
                 "counters_only": None if e2e_co_ms is None else {"value": world * frames * L / (e2e_co_ms * 1e-3) / 1e9, "ms_per_step": e2e_co_ms,
                                                                  "d2h_bytes_per_step": 32, "note": "same call with pred_host = NULL"},
                 "api": "nvd_mc_run_host, NVD_MC_FUSED, pinned host buffers: ONE launch of the fused tcgen05 kernel; info words arrive by sliced H2D copies while it runs (flag per slice), decisions leave by D2H copies queued as the kernel reports slices complete; counters D2H (sliced launches instead under a profiler)"},
-        "gpu_launches": args.steps,
+        # the K fused-kernel launches of the timed region, and the two small kernels of the peer-memory exchange behind them
+        "gpu_launches": args.steps + (2 if (world > 1 and sim.p2p) else 0),
         "clocks": clocks,
         "ber": ber, "frame_errors": int(total_counts[0, 1]), "frames_total": int(total_counts[0, 2]),
         "allreduce_ms": ar_ms,
