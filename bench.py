@@ -9,8 +9,11 @@ decoded information Gbit/s of the (133,171) K=7 code + FNN decoder (14-128-64-32
 A "step" is one pass of the whole hot path over 2^24 frames at one SNR point (2 dB).
   value  : whole-job info Gbit/s of the fused persistent tcgen05 pipeline (no per-frame HBM input:
            frames are a pure function of seed / SNR index / global frame index), CUDA events on the
-           library's stream, max over ranks; the counters' ncclAllReduce is issued by the library on
-           the same stream behind the last launch and is inside the timed region.
+           library's stream, max over ranks; the counters' exchange (NVLink peer memory, or ncclAllReduce) is
+           issued by the library on the same stream behind the last launch and is inside the timed region.
+           Timed region: W warm-up steps, barrier + synchronize, --preroll untimed launches (the clocks sag while
+           the GPU idles in the barrier), one tiny exchange that aligns the ranks on the device, event, exactly K
+           steps, the exchange, event, synchronize, barrier.
   e2e    : same metric through the host-buffer C-ABI call nvd_mc_run_host: info words start in
            pinned HOST memory, decisions + counters end in host memory, copies inside the region.
   --impl reference : the CPU oracle port of the reference path (numpy noise + torch-CPU fp32 MLP,
